@@ -1,0 +1,407 @@
+// Persistent TF32 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (TMEM
+// accumulators, double buffered) -> fused epilogue.  Replaces every cuBLAS/cuDNN call the
+// reference issues for nn.Linear / Conv2d(k=s) / ConvTranspose2d(k=s) on the hot path
+// (reference enhancing/modules/stage1/layers.py:99-101,118-132,168-171,202-205) and their
+// dgrad / wgrad.
+//
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] )                      (per split z)
+//
+// Operand storage ("major"):
+//   a_major = 0 : A is [M, K]        row-major, K contiguous   (K-major)
+//   a_major = 1 : A is [K_total, M]  row-major, M contiguous   (MN-major; wgrad reads dY^T)
+//   b_major = 0 : B is [N, K]        row-major                 (nn.Linear weight)
+//   b_major = 1 : B is [K_total, N]  row-major                 (dgrad reads W, wgrad reads X)
+// Split-K: split z contracts rows/cols [z*K, (z+1)*K) and writes C + z*c_split_stride.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  CG = 2 pairs two CTAs on one
+// 256 x BN tile (tcgen05 cta_group::2): each CTA stages its 128 rows of A and half of B.
+#include "common.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace b200 {
+
+struct GemmParams {
+  int M, N, K;                 // output rows / cols, contraction length per split
+  int num_m_blocks;            // ceil(M / (128*CG)) cluster tiles along M
+  int num_n_blocks;            // ceil(N / BN)
+  int num_splits;
+  int k_blocks;                // ceil(K / 32)
+  float* C;
+  long long ldc, c_split_stride;
+  const float* bias;           // [N] or null
+  const float* res;            // residual added in the epilogue, or null
+  long long ldres;
+  int res_row_mod;             // >0: residual row = row % res_row_mod (positional table)
+  const float* aux;            // tanh'(.) multiplier source: out *= 1 - aux^2, or null
+  long long ldaux;
+  int act;                     // 0 none, 1 tanh
+  int round_out;               // 1: round the stored value to tf32 (it only feeds another GEMM)
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;        // 32 fp32 = one 128-byte swizzle row
+constexpr int kGemmThreads = 192;
+
+template <int BN, int CG>
+struct GemmCfg {
+  static constexpr int BN_CTA = BN / CG;
+  static constexpr int A_BYTES = kBM * kBK * 4;
+  static constexpr int B_BYTES = BN_CTA * kBK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int CG, int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], CG);   // CG producers arrive (the follower arrives remotely)
+      mbar_init(&empty_bar[s], 1);   // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_split = p.num_m_blocks * p.num_n_blocks;
+  const int total_tiles = tiles_per_split * p.num_splits;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        const int z = t / tiles_per_split;
+        const int r = t - z * tiles_per_split;
+        const int mb = r / p.num_n_blocks, nb = r - mb * p.num_n_blocks;
+        const int m0 = (mb * CG + (int)cta_rank) * kBM;
+        const int n0 = nb * BN + (int)cta_rank * Cfg::BN_CTA;
+        const int kbase = z * p.K;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int k0 = kbase + kb * kBK;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if constexpr (AMAJ == 0) tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+            else                     tma_load_3d(sa, &tmA, &full_bar[stage], 0, k0, m0 / 32);
+            if constexpr (BMAJ == 0) tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            else                     tma_load_3d(sb, &tmB, &full_bar[stage], 0, k0, n0 / 32);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            else        mbar_arrive_remote(&full_bar[stage], 0);
+            if constexpr (AMAJ == 0) tma_load_2d_2sm(sa, &tmA, &full_bar[stage], k0, m0);
+            else                     tma_load_3d_2sm(sa, &tmA, &full_bar[stage], 0, k0, m0 / 32);
+            if constexpr (BMAJ == 0) tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, n0);
+            else                     tma_load_3d_2sm(sb, &tmB, &full_bar[stage], 0, k0, n0 / 32);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM * CG, BN, AMAJ, BMAJ);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 32-element column
+      // atoms 4096 B apart (LBO = 32 k-rows x 128 B), 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t A_LBO = AMAJ ? 4096 : 16, B_LBO = BMAJ ? 4096 : 16;
+      constexpr uint32_t A_KSTEP = AMAJ ? 1024 : 32, B_KSTEP = BMAJ ? 1024 : 32;  // bytes per UMMA_K = 8
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024);
+            umma_tf32<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit<CG>(&empty_bar[stage]);  // frees the slot in both CTAs once the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<CG>(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+      const int z = t / tiles_per_split;
+      const int r = t - z * tiles_per_split;
+      const int mb = r / p.num_n_blocks, nb = r - mb * p.num_n_blocks;
+      const int row = (mb * CG + (int)cta_rank) * kBM + q * 32 + lane;
+      const int n0 = nb * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const bool row_ok = row < p.M;
+      float* crow = p.C + (long long)z * p.c_split_stride + (long long)row * p.ldc;
+      const float* rrow = nullptr;
+      if (p.res) rrow = p.res + (long long)(p.res_row_mod > 0 ? row % p.res_row_mod : row) * p.ldres;
+      const float* arow = p.aux ? p.aux + (long long)row * p.ldaux : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+              if (arow) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(arow + col0 + j));
+                o.x *= 1.f - a.x * a.x; o.y *= 1.f - a.y * a.y; o.z *= 1.f - a.z * a.z; o.w *= 1.f - a.w * a.w;
+              }
+              if (rrow) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(rrow + col0 + j));
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1 || leader) mbar_arrive(&tmem_empty[acc]);
+        else                   mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so
+// the library has no link-time dependency on libcuda) and launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr; long long ld; int rows, cols, major, box_mn;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && major == o.major && box_mn == o.box_mn;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.ld); mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.major); mix((size_t)k.box_mn);
+    return h;
+  }
+};
+
+// major 0: matrix [rows = MN extent, cols = K extent], box {32 k, box_mn rows}
+// major 1: matrix [rows = K extent, cols = MN extent], viewed as {32, rows, cols/32}, box {32, 32, box_mn/32}
+static int make_operand_tmap(CUtensorMap* out, const float* ptr, long long ld, int rows, int cols, int major, int box_mn) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, ld, rows, cols, major, box_mn};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(-4, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r;
+  if (major == 0) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_mn};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+    cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
+    cuuint32_t es[3] = {1, 1, 1};
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS)
+    return set_error(-4, "cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d cols=%d major=%d box=%d", (int)r,
+                     ptr, ld, rows, cols, major, box_mn);
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, int CG, int AMAJ, int BMAJ>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_tf32_kernel<BN, CG, AMAJ, BMAJ>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.num_m_blocks * p.num_n_blocks * p.num_splits;
+  int clusters = num_sms() / CG;
+  if (clusters > total) clusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  count_launch();
+  return 0;
+}
+
+template <int BN, int CG>
+static int dispatch_major(int am, int bm, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+  if (am == 0 && bm == 0) return launch_gemm<BN, CG, 0, 0>(a, b, p, s);
+  if (am == 0 && bm == 1) return launch_gemm<BN, CG, 0, 1>(a, b, p, s);
+  if (am == 1 && bm == 1) return launch_gemm<BN, CG, 1, 1>(a, b, p, s);
+  if (am == 1 && bm == 0) return launch_gemm<BN, CG, 1, 0>(a, b, p, s);
+  return set_error(-1, "bad operand major (%d,%d)", am, bm);
+}
+
+int gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major, float* C,
+              long long ldc, int M, int N, int K, int splits, long long c_split_stride, const float* bias,
+              const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux, int act,
+              int round_out, int cta_group, int bn, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits > 0, "gemm: empty problem M=%d N=%d K=%d splits=%d", M, N, K, splits);
+  B200_CHECK_ARG(N % 4 == 0 && ldc % 4 == 0, "gemm: N and ldc must be multiples of 4 (N=%d ldc=%lld)", N, ldc);
+  B200_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "gemm: lda/ldb must be multiples of 4 floats (16-byte TMA strides)");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: operands must be 16-byte aligned");
+  B200_CHECK_ARG(!(a_major == 1 && M % 32), "gemm: MN-major A needs M %% 32 == 0 (M=%d)", M);
+  B200_CHECK_ARG(!(b_major == 1 && N % 32), "gemm: MN-major B needs N %% 32 == 0 (N=%d)", N);
+  B200_CHECK_ARG(splits == 1 || K % 32 == 0, "gemm: split-K needs K %% 32 == 0");
+  B200_CHECK_ARG(!res || ldres % 4 == 0, "gemm: ldres %% 4");
+  B200_CHECK_ARG(!aux || ldaux % 4 == 0, "gemm: ldaux %% 4");
+  if (cta_group != 2) cta_group = 1;
+  if (bn <= 0) bn = N >= 256 ? 256 : (N > 128 ? (N <= 192 ? 192 : 256) : (N > 64 ? 128 : 64));
+  B200_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256, "gemm: unsupported BN %d", bn);
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_blocks = (M + kBM * cta_group - 1) / (kBM * cta_group);
+  p.num_n_blocks = (N + bn - 1) / bn;
+  p.num_splits = splits;
+  p.k_blocks = (K + kBK - 1) / kBK;
+  p.C = C; p.ldc = ldc; p.c_split_stride = c_split_stride;
+  p.bias = bias; p.res = res; p.ldres = ldres; p.res_row_mod = res_row_mod;
+  p.aux = aux; p.ldaux = ldaux; p.act = act; p.round_out = round_out;
+
+  CUtensorMap tmA, tmB;
+  const int ktot = K * splits;
+  int rc;
+  if (a_major == 0) rc = make_operand_tmap(&tmA, A, lda, M, ktot, 0, kBM);
+  else              rc = make_operand_tmap(&tmA, A, lda, ktot, M, 1, kBM);
+  if (rc) return rc;
+  const int bn_cta = bn / cta_group;
+  if (b_major == 0) rc = make_operand_tmap(&tmB, B, ldb, N, ktot, 0, bn_cta);
+  else              rc = make_operand_tmap(&tmB, B, ldb, ktot, N, 1, bn_cta);
+  if (rc) return rc;
+
+#define B200_GEMM_CASE(BN_)                                                                         \
+  case BN_:                                                                                         \
+    return cta_group == 2 ? dispatch_major<BN_, 2>(a_major, b_major, tmA, tmB, p, stream)           \
+                          : dispatch_major<BN_, 1>(a_major, b_major, tmA, tmB, p, stream);
+  switch (bn) {
+    B200_GEMM_CASE(64)
+    B200_GEMM_CASE(128)
+    B200_GEMM_CASE(192)
+    B200_GEMM_CASE(256)
+  }
+#undef B200_GEMM_CASE
+  return set_error(-1, "gemm: unreachable");
+}
+
+}  // namespace b200

@@ -1,0 +1,363 @@
+// HBM-bound row-wise kernels around the GEMMs: LayerNorm forward/backward
+// (reference layers.py:85-92,143,150), patch <-> image re-layout for the kernel==stride
+// convolutions (layers.py:168-171,202-205), column sums (bias gradients), split-K reduction
+// and tf32 rounding of GEMM operands.  All are coalesced float4 streams sized to the SM count.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr float kLnEps = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row held in registers (NV float4 per lane, D <= 128*NV)
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
+              int round_out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 2;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      v[i] = c < nv ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, d = v[i].w - mu;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + kLnEps);
+    float4* yr = reinterpret_cast<float4*>(y + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        float4 o;
+        o.x = (v[i].x - mu) * rstd * g.x + b.x;
+        o.y = (v[i].y - mu) * rstd * g.y + b.y;
+        o.z = (v[i].z - mu) * rstd * g.z + b.z;
+        o.w = (v[i].w - mu) * rstd * g.w + b.w;
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        yr[c] = o;
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// LayerNorm backward.  dx = rstd * (dy*g - mean(dy*g) - xh * mean(dy*g*xh)) [+ dres];
+// per-CTA partial sums of dgamma = sum dy*xh and dbeta = sum dy go to part[blk][2][D].
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+              float* __restrict__ dx, float* __restrict__ part, int M, int D, int round_out) {
+  extern __shared__ float sm[];   // [warps][2][D]
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = D >> 2;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    const float4* gr = reinterpret_cast<const float4*>(dy + (size_t)row * D);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 xv = xr[c];
+        const float4 d = gr[c];
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      } else {
+        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[i] = xh[i];
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+    float4* outr = reinterpret_cast<float4*>(dx + (size_t)row * D);
+    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * D) : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (g[i].x - m1 - xh[i].x * m2);
+        o.y = rs * (g[i].y - m1 - xh[i].y * m2);
+        o.z = rs * (g[i].z - m1 - xh[i].z * m2);
+        o.w = rs * (g[i].w - m1 - xh[i].w * m2);
+        if (rr) { const float4 r = rr[c]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        outr[c] = o;
+      }
+    }
+  }
+  // CTA-level reduction of the per-warp column partials
+  float* sg = sm + (size_t)warp * 2 * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      reinterpret_cast<float4*>(sg)[c] = dg[i];
+      reinterpret_cast<float4*>(sg + D)[c] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) a += sm[(size_t)w * 2 * D + j];
+    part[(size_t)blockIdx.x * 2 * D + j] = a;
+  }
+}
+
+// out[j] = sum_i part[i][j], j < n  (deterministic second stage)
+__global__ void colpart_reduce_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float a = 0.f;
+  for (int i = 0; i < nparts; ++i) a += part[(size_t)i * n + j];
+  out[j] = a;
+}
+
+// part is [nparts][2][D] -> dgamma[D], dbeta[D]
+__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * D) return;
+  float a = 0.f;
+  for (int i = 0; i < nparts; ++i) a += part[(size_t)i * 2 * D + j];
+  if (j < D) dgamma[j] = a; else dbeta[j - D] = a;
+}
+
+// column sums of X[M, N] (bias gradients): stage 1 writes part[blk][N]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ part) {
+  // block = 32 x 8 threads: threadIdx.x spans 32 float4 columns, threadIdx.y strides rows
+  __shared__ float4 sm[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nv = N >> 2;
+  for (int cb = 0; cb < nv; cb += 32) {
+    const int c = cb + tx;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv)
+      for (int r = blockIdx.x * 8 + ty; r < M; r += gridDim.x * 8) {
+        const float4 v = *reinterpret_cast<const float4*>(X + (size_t)r * ld + c * 4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < nv) {
+      float4 s = sm[0][tx];
+      for (int w = 1; w < 8; ++w) { s.x += sm[w][tx].x; s.y += sm[w][tx].y; s.z += sm[w][tx].z; s.w += sm[w][tx].w; }
+      *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * N + c * 4) = s;
+    }
+    __syncthreads();
+  }
+}
+
+// out[i] = sum_z part[z][i] (+ bias-free), used after split-K wgrad
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long n4, long long stride4,
+                                     float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(part)[i];
+    for (int z = 1; z < splits; ++z) {
+      const float4 v = reinterpret_cast<const float4*>(part)[i + z * stride4];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+// img [B,C,H,W] -> patches [B*gh*gw, C*p*p] with the patch vector ordered (c, ph, pw): the
+// im2col of Conv2d(kernel=stride=p) followed by 'b c h w -> b (h w) c' (layers.py:168-171).
+// p % 4 == 0 so that one float4 stays inside a patch row.
+__global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int H, int W, int p,
+                                int round_out) {
+  const int gh = H / p, gw = W / p;
+  const int pd = C * p * p;
+  const long long total4 = (long long)B * gh * gw * pd / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    // iterate in *image* order so that global reads are fully coalesced; writes are 16-byte pieces
+    const long long e = i * 4;
+    const int w = (int)(e % W);
+    long long r = e / W;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    float4 v = reinterpret_cast<const float4*>(img)[i];
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    const int hp = h / p, ph = h % p, wp = w / p, pw = w % p;
+    const long long row = ((long long)b * gh + hp) * gw + wp;
+    *reinterpret_cast<float4*>(out + row * pd + (c * p + ph) * p + pw) = v;
+  }
+}
+
+// tokens [B*gh*gw, C*p*p] (+ bias[c]) -> img [B,C,H,W]: the pixel-shuffle store of
+// ConvTranspose2d(kernel=stride=p) after 'b (h w) c -> b c h w' (layers.py:202-205).
+// With bias == nullptr and the roles swapped it is also the backward of patchify.
+__global__ void unpatchify_kernel(const float* __restrict__ tok, const float* __restrict__ bias, float* __restrict__ img,
+                                  int B, int C, int H, int W, int p) {
+  const int gh = H / p, gw = W / p;
+  const int pd = C * p * p;
+  const long long total4 = (long long)B * C * H * W / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int w = (int)(e % W);
+    long long r = e / W;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const int hp = h / p, ph = h % p, wp = w / p, pw = w % p;
+    const long long row = ((long long)b * gh + hp) * gw + wp;
+    float4 v = *reinterpret_cast<const float4*>(tok + row * pd + (c * p + ph) * p + pw);
+    if (bias) { const float bb = __ldg(bias + c); v.x += bb; v.y += bb; v.z += bb; v.w += bb; }
+    reinterpret_cast<float4*>(img)[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int stream_grid(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <int NV>
+static void ln_fwd_launch(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int M, int D,
+                          int round_out, cudaStream_t s) {
+  const int blocks = stream_grid((long long)M * 32, 256);
+  ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, g, b, y, mean, rstd, M, D, round_out);
+}
+
+int layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M,
+                      int D, int round_out, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm: need D %% 4 == 0 and D <= 2048 (D=%d)", D);
+  const int nv = (D + 127) / 128;
+  if (nv <= 1) ln_fwd_launch<1>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 2) ln_fwd_launch<2>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 4) ln_fwd_launch<4>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 6) ln_fwd_launch<6>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 10) ln_fwd_launch<10>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  else ln_fwd_launch<16>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  B200_LAUNCH_OK("ln_fwd_kernel");
+  return 0;
+}
+
+int layernorm_bwd_blocks() { return num_sms() * 2; }
+size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)layernorm_bwd_blocks() * 2 * D * sizeof(float); }
+
+template <int NV>
+static int ln_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* dres, float* dx, float* part, int M, int D, int round_out, int blocks, cudaStream_t s) {
+  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  auto kern = ln_bwd_kernel<NV>;
+  if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, 256, smem, s>>>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out);
+  return 0;
+}
+
+int layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* dres, float* dx, float* dgamma, float* dbeta, int M, int D, int round_out,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm: need D %% 4 == 0 and D <= 2048 (D=%d)", D);
+  B200_CHECK_ARG(ws_bytes >= layernorm_bwd_workspace_bytes(D), "layernorm_backward: workspace too small");
+  int blocks = layernorm_bwd_blocks();
+  if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
+  float* part = static_cast<float*>(workspace);
+  const int nv = (D + 127) / 128;
+  int rc;
+  if (nv <= 1) rc = ln_bwd_launch<1>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  else if (nv <= 2) rc = ln_bwd_launch<2>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  else if (nv <= 4) rc = ln_bwd_launch<4>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  else if (nv <= 6) rc = ln_bwd_launch<6>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  else if (nv <= 10) rc = ln_bwd_launch<10>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  else rc = ln_bwd_launch<16>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  if (rc) return rc;
+  B200_LAUNCH_OK("ln_bwd_kernel");
+  ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, stream>>>(part, blocks, D, dgamma, dbeta);
+  B200_LAUNCH_OK("ln_param_reduce_kernel");
+  return 0;
+}
+
+int colsum_blocks() { return num_sms() * 2; }
+size_t colsum_workspace_bytes(int N) { return (size_t)colsum_blocks() * N * sizeof(float); }
+
+int colsum(const float* X, long long ld, int M, int N, float* out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && N > 0 && N % 4 == 0 && ld % 4 == 0, "colsum: N and ld must be multiples of 4");
+  B200_CHECK_ARG(ws_bytes >= colsum_workspace_bytes(N), "colsum: workspace too small");
+  int blocks = colsum_blocks();
+  if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
+  float* part = static_cast<float*>(workspace);
+  colsum_kernel<<<blocks, 256, 0, stream>>>(X, ld, M, N, part);
+  B200_LAUNCH_OK("colsum_kernel");
+  colpart_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(part, blocks, N, out);
+  B200_LAUNCH_OK("colpart_reduce_kernel");
+  return 0;
+}
+
+int splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, cudaStream_t stream) {
+  B200_CHECK_ARG(n % 4 == 0 && split_stride % 4 == 0, "splitk_reduce: sizes must be multiples of 4");
+  splitk_reduce_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(part, splits, n / 4, split_stride / 4, out);
+  B200_LAUNCH_OK("splitk_reduce_kernel");
+  return 0;
+}
+
+int round_tf32_copy(const float* in, float* out, long long n, cudaStream_t stream) {
+  B200_CHECK_ARG(n % 4 == 0, "round_tf32: n %% 4");
+  round_tf32_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(in, out, n / 4);
+  B200_LAUNCH_OK("round_tf32_kernel");
+  return 0;
+}
+
+int patchify(const float* img, float* out, int B, int C, int H, int W, int p, int round_out, cudaStream_t stream) {
+  B200_CHECK_ARG(p % 4 == 0 && H % p == 0 && W % p == 0, "patchify: patch must be a multiple of 4 and divide the image");
+  patchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(img, out, B, C, H, W, p, round_out);
+  B200_LAUNCH_OK("patchify_kernel");
+  return 0;
+}
+
+int unpatchify(const float* tok, const float* bias, float* img, int B, int C, int H, int W, int p, cudaStream_t stream) {
+  B200_CHECK_ARG(p % 4 == 0 && H % p == 0 && W % p == 0, "unpatchify: patch must be a multiple of 4 and divide the image");
+  unpatchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(tok, bias, img, B, C, H, W, p);
+  B200_LAUNCH_OK("unpatchify_kernel");
+  return 0;
+}
+
+}  // namespace b200

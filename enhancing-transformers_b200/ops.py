@@ -1,0 +1,204 @@
+"""Tensor-level wrappers over the C ABI (include/b200vq.h).  PyTorch is plumbing here: it owns
+device memory (caching allocator) and the current stream; every FLOP below runs in
+libb200vq.so.  CPU tensors are rejected -- there is no CPU path."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _req(t: Optional[Tensor], name: str, dtype=torch.float32) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"b200vq: `{name}` is on {t.device}; this implementation has no CPU path "
+                           "(use the reference modules on CPU)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"b200vq: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"b200vq: `{name}` must be contiguous")
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(_lib.lib().b200vq_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_major: int = 0, b_major: int = 0,
+         lda: Optional[int] = None, ldb: Optional[int] = None, out: Optional[Tensor] = None,
+         bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_row_mod: int = 0,
+         aux: Optional[Tensor] = None, act: int = 0, round_out: bool = False, splits: int = 1,
+         cta_group: int = 1, bn: int = 0) -> Tensor:
+    """C[M,N] = epilogue(A . B^T).  See b200vq_gemm_tf32.  With splits > 1 returns [splits, M, N]."""
+    _req(a, "a"); _req(b, "b"); _req(bias, "bias"); _req(res, "res"); _req(aux, "aux")
+    if lda is None:
+        lda = a.shape[-1]
+    if ldb is None:
+        ldb = b.shape[-1]
+    if out is None:
+        out = torch.empty((splits, M, N) if splits > 1 else (M, N), device=a.device, dtype=torch.float32)
+    _req(out, "out")
+    rc = _lib.lib().b200vq_gemm_tf32(_p(a), lda, a_major, _p(b), ldb, b_major, _p(out), N, M, N, K, splits, M * N,
+                                     _p(bias), _p(res), (res.shape[-1] if res is not None else 0), res_row_mod,
+                                     _p(aux), (aux.shape[-1] if aux is not None else 0), act, int(round_out),
+                                     cta_group, bn, _stream())
+    _lib.check(rc, "gemm_tf32")
+    return out
+
+
+def splitk_reduce(part: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    _req(part, "part")
+    splits = part.shape[0]
+    n = part[0].numel()
+    if out is None:
+        out = torch.empty(part.shape[1:], device=part.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_splitk_reduce(_p(part), splits, n, n, _p(out), _stream()), "splitk_reduce")
+    return out
+
+
+def pick_splits(k_total: int, out_rows: int, out_cols: int, sms: int = 148) -> int:
+    """split count for a wgrad GEMM: enough (tile x split) work items to fill the SMs twice,
+    each split contracting a multiple of 32."""
+    tiles = -(-out_rows // 128) * -(-out_cols // 256)
+    want = max(1, (2 * sms + tiles - 1) // tiles)
+    s = 1
+    while s * 2 <= want and k_total % (s * 2 * 32) == 0 and k_total // (s * 2) >= 256:
+        s *= 2
+    return s
+
+
+# ------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, round_out: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    D = x.shape[-1]
+    M = x.numel() // D
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D,
+                                               int(round_out), _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
+                  round_out: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    _req(dy, "dy"); _req(x, "x"); _req(dres, "dres")
+    D = x.shape[-1]
+    M = x.numel() // D
+    L = _lib.lib()
+    ws_bytes = L.b200vq_layernorm_bwd_workspace_bytes(D)
+    ws = torch.empty(ws_bytes // 4, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
+    dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
+    _lib.check(L.b200vq_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma),
+                                      _p(dbeta), M, D, int(round_out), _p(ws), ws_bytes, _stream()), "layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------- attention
+def attention_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float, round_out: bool) -> Tuple[Tensor, Tensor]:
+    _req(qkv, "qkv")
+    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_attention_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, dh, scale, int(round_out),
+                                               _stream()), "attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, heads: int, dh: int,
+                  scale: float, round_out: bool) -> Tensor:
+    _req(qkv, "qkv"); _req(out, "out"); _req(lse, "lse"); _req(dout, "dout")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _lib.check(_lib.lib().b200vq_attention_bwd(_p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(delta), B, N, heads, dh,
+                                               scale, int(round_out), _stream()), "attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------- quantiser
+def vq_fwd(z: Tensor, E: Tensor, depth: int, beta: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """z [..., D], E [K, D] -> (straight-through value like z, loss scalar, idx int64 [M, depth])"""
+    _req(z, "z"); _req(E, "embedding.weight")
+    K, D = E.shape
+    M = z.numel() // D
+    L = _lib.lib()
+    ws_bytes = L.b200vq_vq_workspace_bytes(M, K, depth)
+    ws = torch.empty(ws_bytes // 4, device=z.device, dtype=torch.float32)
+    out = torch.empty_like(z)
+    idx = torch.empty(M, depth, device=z.device, dtype=torch.int64)
+    loss = torch.empty((), device=z.device, dtype=torch.float32)
+    _lib.check(L.b200vq_vq_fwd(_p(z), _p(E), _p(out), _p(idx), _p(loss), M, K, D, depth, float(beta), _p(ws), ws_bytes,
+                               _stream()), "vq_fwd")
+    return out, loss, idx
+
+
+def vq_bwd(z: Tensor, E: Tensor, idx: Tensor, g_out: Optional[Tensor], g_loss: Optional[Tensor], residual: bool,
+           beta: float) -> Tuple[Tensor, Tensor]:
+    _req(z, "z"); _req(E, "embedding.weight"); _req(idx, "idx", torch.int64); _req(g_out, "g_out"); _req(g_loss, "g_loss")
+    K, D = E.shape
+    M = z.numel() // D
+    depth = idx.shape[-1] if idx.dim() == 2 else 1
+    gz = torch.empty_like(z)
+    gE = torch.empty_like(E)
+    _lib.check(_lib.lib().b200vq_vq_bwd(_p(z), _p(E), _p(idx), _p(g_out), _p(g_loss), _p(gz), _p(gE), M, K, D, depth,
+                                        int(residual), float(beta), _stream()), "vq_bwd")
+    return gz, gE
+
+
+def vq_embed(E: Tensor, codes: Tensor, depth: int) -> Tensor:
+    _req(E, "embedding.weight"); _req(codes, "codes", torch.int64)
+    K, D = E.shape
+    M = codes.numel() // depth
+    out = torch.empty(M, D, device=E.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_vq_embed(_p(E), _p(codes), _p(out), M, K, D, depth, _stream()), "vq_embed")
+    return out
+
+
+# ---------------------------------------------------------------------------- layout / reductions
+def patchify(img: Tensor, p: int, round_out: bool) -> Tensor:
+    _req(img, "img")
+    B, C, H, W = img.shape
+    out = torch.empty(B * (H // p) * (W // p), C * p * p, device=img.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_patchify(_p(img), _p(out), B, C, H, W, p, int(round_out), _stream()), "patchify")
+    return out
+
+
+def unpatchify(tok: Tensor, bias: Optional[Tensor], B: int, C: int, H: int, W: int, p: int) -> Tensor:
+    _req(tok, "tok"); _req(bias, "bias")
+    img = torch.empty(B, C, H, W, device=tok.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_unpatchify(_p(tok), _p(bias), _p(img), B, C, H, W, p, _stream()), "unpatchify")
+    return img
+
+
+def colsum(x: Tensor) -> Tensor:
+    _req(x, "x")
+    N = x.shape[-1]
+    M = x.numel() // N
+    L = _lib.lib()
+    ws_bytes = L.b200vq_colsum_workspace_bytes(N)
+    ws = torch.empty(ws_bytes // 4, device=x.device, dtype=torch.float32)
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    _lib.check(L.b200vq_colsum(_p(x), N, M, N, _p(out), _p(ws), ws_bytes, _stream()), "colsum")
+    return out
+
+
+def round_tf32(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    _req(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().b200vq_round_tf32(_p(x), _p(out), x.numel(), _stream()), "round_tf32")
+    return out
