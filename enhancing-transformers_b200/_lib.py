@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b200vq_colsum_workspace_bytes": (c_sz, [c_i]),
     "b200vq_colsum": (c_i, [c_f, c_ll, c_i, c_i, c_f, c_f, c_sz, c_f]),
     "b200vq_round_tf32": (c_i, [c_f, c_f, c_ll, c_f]),
+    "b200vq_add_rows_mod": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_f]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

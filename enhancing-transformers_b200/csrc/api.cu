@@ -54,6 +54,7 @@ int unpatchify(const float*, const float*, float*, int, int, int, int, int, cuda
 size_t colsum_workspace_bytes(int);
 int colsum(const float*, long long, int, int, float*, void*, size_t, cudaStream_t);
 int round_tf32_copy(const float*, float*, long long, cudaStream_t);
+int add_rows_mod(const float*, const float*, float*, long long, int, int, cudaStream_t);
 
 }  // namespace b200
 
@@ -118,5 +119,9 @@ int b200vq_colsum(const float* X, long long ld, int M, int N, float* out, void* 
   return colsum(X, ld, M, N, out, workspace, ws_bytes, S(stream));
 }
 int b200vq_round_tf32(const float* in, float* out, long long n, void* stream) { return round_tf32_copy(in, out, n, S(stream)); }
+
+int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream) {
+  return add_rows_mod(x, table, out, M, D, R, S(stream));
+}
 
 }  // extern "C"

@@ -214,13 +214,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   bits [0,14)  start address >> 4      bits [16,30) leading-dim byte offset >> 4
 //   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1
 //   bits [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//                (1 = SWIZZLE_128B_BASE32B: 32-byte chunks XOR (row % 4) -- the only layout
+//                 tcgen05 accepts for MN-major tf32 operands; TMA: SWIZZLE_128B_ATOM_32B)
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // instruction descriptor for kind::tf32, fp32 accumulate (upper 32 bits of the 64-bit idesc):

@@ -139,9 +139,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------------------------------------------------------- MMA issuer
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM * CG, BN, AMAJ, BMAJ);
-      // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 32-element column
-      // atoms 4096 B apart (LBO = 32 k-rows x 128 B), 8-k-row groups 1024 B apart (SBO).
+      // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), LBO unused.
+      // MN-major (SWIZZLE_128B_BASE32B, mandatory for tf32): smem holds [mn atom of 32][32 k-rows][128 B];
+      // atoms 4096 B apart (LBO), 4-k-row swizzle groups 512 B apart (SBO).
       constexpr uint32_t A_LBO = AMAJ ? 4096 : 16, B_LBO = BMAJ ? 4096 : 16;
+      constexpr uint32_t A_SBO = AMAJ ? 512 : 1024, B_SBO = BMAJ ? 512 : 1024;
+      constexpr uint32_t A_LAY = AMAJ ? kLayoutSw128Base32 : kLayoutSw128, B_LAY = BMAJ ? kLayoutSw128Base32 : kLayoutSw128;
       constexpr uint32_t A_KSTEP = AMAJ ? 1024 : 32, B_KSTEP = BMAJ ? 1024 : 32;  // bytes per UMMA_K = 8
       int stage = 0;
       uint32_t phase = 0;
@@ -159,8 +162,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
-            const uint64_t bd = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024);
+            const uint64_t ad = make_smem_desc(sa + k * A_KSTEP, A_LBO, A_SBO, A_LAY);
+            const uint64_t bd = make_smem_desc(sb + k * B_KSTEP, B_LBO, B_SBO, B_LAY);
             umma_tf32<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
           umma_commit<CG>(&empty_bar[stage]);  // frees the slot in both CTAs once the MMAs retire
@@ -301,7 +304,7 @@ static int make_operand_tmap(CUtensorMap* out, const float* ptr, long long ld, i
     cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
     cuuint32_t es[3] = {1, 1, 1};
     r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS)
@@ -323,10 +326,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   const int total = p.num_m_blocks * p.num_n_blocks * p.num_splits;
-  int clusters = num_sms() / CG;
-  if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * CG);
+  cfg.gridDim = dim3((num_sms() / CG) * CG);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -337,6 +338,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent kernel: launch exactly as many clusters as can be co-resident (a CTA pair needs
+  // two free SMs of one TPC; fewer than num_sms/2 pairs may fit) so that no cluster waits for
+  // a second wave behind CTAs that never exit early
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = num_sms() / CG;
+    max_clusters = n;
+  }
+  int clusters = max_clusters < total ? max_clusters : total;
+  cfg.gridDim = dim3(clusters * CG);
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   count_launch();
   return 0;

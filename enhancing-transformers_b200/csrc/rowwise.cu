@@ -203,6 +203,20 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
   }
 }
 
+// out[m,:] = x[m,:] + table[m % R,:]  (decoder positional add, layers.py:210)
+__global__ void add_rows_mod_kernel(const float* __restrict__ x, const float* __restrict__ table, float* __restrict__ out,
+                                    long long M, int D4, int R) {
+  const long long total = M * D4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / D4;
+    const int c = (int)(i - m * D4);
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 t = __ldg(reinterpret_cast<const float4*>(table) + (m % R) * D4 + c);
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 // img [B,C,H,W] -> patches [B*gh*gw, C*p*p] with the patch vector ordered (c, ph, pw): the
 // im2col of Conv2d(kernel=stride=p) followed by 'b c h w -> b (h w) c' (layers.py:168-171).
 // p % 4 == 0 so that one float4 stays inside a patch row.
@@ -343,6 +357,13 @@ int round_tf32_copy(const float* in, float* out, long long n, cudaStream_t strea
   B200_CHECK_ARG(n % 4 == 0, "round_tf32: n %% 4");
   round_tf32_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(in, out, n / 4);
   B200_LAUNCH_OK("round_tf32_kernel");
+  return 0;
+}
+
+int add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, cudaStream_t stream) {
+  B200_CHECK_ARG(D % 4 == 0 && R > 0 && M > 0, "add_rows_mod: D %% 4 and R > 0 required");
+  add_rows_mod_kernel<<<stream_grid(M * (D / 4), 256), 256, 0, stream>>>(x, table, out, M, D / 4, R);
+  B200_LAUNCH_OK("add_rows_mod_kernel");
   return 0;
 }
 

@@ -1,0 +1,270 @@
+"""autograd.Functions that stitch the C-ABI kernels into the forward/backward of the ViT blocks
+and the quantiser.  Each Function is one fused unit whose saved tensors were chosen for HBM
+footprint (SURVEY.md section 7 'Memory at config 2'): LayerNorm statistics, one copy of qkv, the
+attention output and its log-sum-exp (never the N x N probabilities), the tanh output.
+
+Precision.  Tensor-core GEMMs are tcgen05 kind::tf32 (fp32 accumulate).  The hardware truncates
+fp32 operands to tf32, which would bias every product low; operands are therefore rounded to
+nearest once, where they are produced (`round_out=True` on the producing kernel) or, for
+parameters, in a cached shadow copy that is refreshed when the parameter's version counter
+changes."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+# cta_group used for the big GEMMs (2 = CTA pair per 256-row tile); a module-level switch so
+# that tests and bench.py can pin it
+GEMM_CTA_GROUP = 1
+
+_shadow: Dict[Tuple[int, int], Tuple[int, Tensor]] = {}
+
+
+def tf32_shadow(w: Tensor) -> Tensor:
+    """tf32-rounded copy of a parameter, cached per (storage address, numel) and refreshed when
+    the parameter's version counter moves (optimizer steps bump it)."""
+    key = (w.data_ptr(), w.numel())
+    ent = _shadow.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    src = w.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    out = ops.round_tf32(src, ent[1] if ent is not None and ent[1].shape == src.shape else None)
+    _shadow[key] = (ver, out)
+    return out
+
+
+def clear_shadow_cache() -> None:
+    _shadow.clear()
+
+
+def _wgrad(dy: Tensor, x: Tensor, rows: int, cols: int) -> Tensor:
+    """dW[rows, cols] = dy[M, rows]^T . x[M, cols]   (both operands MN-major, split-K)"""
+    M = dy.shape[0]
+    splits = ops.pick_splits(M, rows, cols)
+    part = ops.gemm(dy, x, rows, cols, M // splits, a_major=1, b_major=1, splits=splits, cta_group=GEMM_CTA_GROUP)
+    return ops.splitk_reduce(part) if splits > 1 else part
+
+
+class TransformerLayerFn(torch.autograd.Function):
+    """x -> attn(LN(x)) + x -> ff(LN(.)) + .   (reference layers.py:145-148 with :85-132)"""
+
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, w_qkv, w_out, b_out, ln2_w, ln2_b, w1, b1, w2, b2, B, N, heads, dh):
+        cg = GEMM_CTA_GROUP
+        M, D = x.shape
+        inner = heads * dh
+        mlp = w1.shape[0]
+        scale = dh ** -0.5
+        wq, wo, w1r, w2r = tf32_shadow(w_qkv), tf32_shadow(w_out), tf32_shadow(w1), tf32_shadow(w2)
+        h1, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, True)
+        qkv = ops.gemm(h1, wq, M, 3 * inner, D, round_out=True, cta_group=cg)
+        o, lse = ops.attention_fwd(qkv, B, N, heads, dh, scale, True)
+        x1 = ops.gemm(o, wo, M, D, inner, bias=b_out, res=x, cta_group=cg)
+        h2, mean2, rstd2 = ops.layernorm_fwd(x1, ln2_w, ln2_b, True)
+        t = ops.gemm(h2, w1r, M, mlp, D, bias=b1, act=1, round_out=True, cta_group=cg)
+        x2 = ops.gemm(t, w2r, M, D, mlp, bias=b2, res=x1, cta_group=cg)
+        ctx.save_for_backward(x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, w_qkv, w_out, ln2_w, w1, w2)
+        ctx.dims = (B, N, heads, dh)
+        return x2
+
+    @staticmethod
+    def backward(ctx, g):
+        cg = GEMM_CTA_GROUP
+        x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, w_qkv, w_out, ln2_w, w1, w2 = ctx.saved_tensors
+        B, N, heads, dh = ctx.dims
+        M, D = x.shape
+        inner = heads * dh
+        mlp = w1.shape[0]
+        scale = dh ** -0.5
+        g = g.contiguous()
+        wq, wo, w1r, w2r = tf32_shadow(w_qkv), tf32_shadow(w_out), tf32_shadow(w1), tf32_shadow(w2)
+        # ---- feed-forward branch
+        db2 = ops.colsum(g)
+        dw2 = _wgrad(g, t, D, mlp)
+        dt = ops.gemm(g, w2r, M, mlp, D, b_major=1, aux=t, round_out=True, cta_group=cg)     # (g W2) * (1 - t^2)
+        db1 = ops.colsum(dt)
+        dw1 = _wgrad(dt, h2, mlp, D)
+        dh2 = ops.gemm(dt, w1r, M, D, mlp, b_major=1, cta_group=cg)
+        del dt
+        g1, dln2_w, dln2_b = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2_w, g)
+        del dh2
+        # ---- attention branch
+        dbo = ops.colsum(g1)
+        dwo = _wgrad(g1, o, D, inner)
+        do = ops.gemm(g1, wo, M, inner, D, b_major=1, round_out=True, cta_group=cg)
+        dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, True)
+        del do
+        dwq = _wgrad(dqkv, h1, 3 * inner, D)
+        dh1 = ops.gemm(dqkv, wq, M, D, 3 * inner, b_major=1, cta_group=cg)
+        del dqkv
+        gx, dln1_w, dln1_b = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, g1)
+        return gx, dln1_w, dln1_b, dwq, dwo, dbo, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(dim) (reference layers.py:143,150)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, round_out):
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, bool(round_out))
+        ctx.save_for_backward(x, mean, rstd, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, rstd, w = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, w, None)
+        return dx, dw, db, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) (+ res): stand-alone GEMM unit used by the sub-modules when they are
+    called outside the fused layer (reference layers.py:99-101,118,120)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, round_out):
+        M, K = x.shape
+        N = w.shape[0]
+        xr = ops.round_tf32(x)
+        y = ops.gemm(xr, tf32_shadow(w), M, N, K, bias=b, act=int(act), round_out=bool(round_out), cta_group=GEMM_CTA_GROUP)
+        ctx.save_for_backward(xr, w, y if act else None)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xr, w, y = ctx.saved_tensors
+        M, K = xr.shape
+        N = w.shape[0]
+        g = g.contiguous()
+        if y is not None:   # tanh backward folded into an elementwise pass of the dgrad epilogue is
+            g = g * (1 - y * y)   # only available fused (TransformerLayerFn); stand-alone path keeps it simple
+        gr = ops.round_tf32(g)
+        db = ops.colsum(gr) if ctx.has_bias else None
+        dw = _wgrad(gr, xr, N, K)
+        dx = ops.gemm(gr, tf32_shadow(w), M, K, N, b_major=1, cta_group=GEMM_CTA_GROUP)
+        return dx, dw, db, None, None
+
+
+class AttentionCoreFn(torch.autograd.Function):
+    """softmax(q k^T * scale) v on the packed qkv matrix (reference layers.py:124-130)"""
+
+    @staticmethod
+    def forward(ctx, qkv, B, N, heads, dh):
+        scale = dh ** -0.5
+        qr = ops.round_tf32(qkv)
+        o, lse = ops.attention_fwd(qr, B, N, heads, dh, scale, False)
+        ctx.save_for_backward(qr, o, lse)
+        ctx.dims = (B, N, heads, dh)
+        return o
+
+    @staticmethod
+    def backward(ctx, g):
+        qr, o, lse = ctx.saved_tensors
+        B, N, heads, dh = ctx.dims
+        dqkv = ops.attention_bwd(qr, o, lse, ops.round_tf32(g.contiguous()), B, N, heads, dh, dh ** -0.5, False)
+        return dqkv, None, None, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv2d(C, D, k=s=p) + 'b c h w -> b (h w) c' + positional table
+    (reference layers.py:168-172,178-179) as one GEMM over the im2col view."""
+
+    @staticmethod
+    def forward(ctx, img, w, b, pos, p):
+        B, C, H, W = img.shape
+        D = w.shape[0]
+        n_tok = (H // p) * (W // p)
+        patches = ops.patchify(img, p, True)
+        M, pd = patches.shape
+        x = ops.gemm(patches, tf32_shadow(w).view(D, pd), M, D, pd, bias=b, res=pos.view(n_tok, D), res_row_mod=n_tok,
+                     cta_group=GEMM_CTA_GROUP)
+        ctx.save_for_backward(patches, w)
+        ctx.geom = (B, C, H, W, p)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        patches, w = ctx.saved_tensors
+        B, C, H, W, p = ctx.geom
+        D = w.shape[0]
+        M, pd = patches.shape
+        g = g.contiguous()
+        db = ops.colsum(g)
+        dw = _wgrad(g, patches, D, pd).view_as(w)
+        dimg = None
+        if ctx.needs_input_grad[0]:
+            dpat = ops.gemm(g, tf32_shadow(w).view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
+            dimg = ops.unpatchify(dpat, None, B, C, H, W, p)
+        return dimg, dw, db, None, None
+
+
+class ToPixelFn(torch.autograd.Function):
+    """'b (h w) c -> b c h w' + ConvTranspose2d(D, C, k=s=p) (reference layers.py:202-205,212)
+    as one GEMM plus a pixel-shuffle store."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, B, H, W, p):
+        M, D = x.shape
+        C = w.shape[1]
+        pd = C * p * p
+        y = ops.gemm(x, tf32_shadow(w).view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
+        img = ops.unpatchify(y, b, B, C, H, W, p)
+        ctx.save_for_backward(x, w)
+        ctx.geom = (B, C, H, W, p)
+        return img
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, C, H, W, p = ctx.geom
+        M, D = x.shape
+        pd = C * p * p
+        dy = ops.patchify(g.contiguous(), p, True)
+        db = ops.colsum(dy).view(C, p * p).sum(dim=1)
+        dw = _wgrad(x, dy, D, pd).view_as(w)
+        dx = ops.gemm(dy, tf32_shadow(w).view(D, pd), M, D, pd, cta_group=GEMM_CTA_GROUP)
+        return dx, dw, db, None, None, None, None
+
+
+class AddPosFn(torch.autograd.Function):
+    """token + de_pos_embedding (reference layers.py:210)"""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        return ops.add_rows_mod(x, pos)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class VectorQuantizeFn(torch.autograd.Function):
+    """BaseQuantizer.forward + VectorQuantizer.quantize (reference quantizers.py:38-63,74-92)."""
+
+    @staticmethod
+    def forward(ctx, z, E, depth, beta, residual):
+        out, loss, idx = ops.vq_fwd(z, E, depth, beta)
+        ctx.save_for_backward(z, E, idx)
+        ctx.cfg = (depth, beta, residual)
+        ctx.mark_non_differentiable(idx)
+        return out, loss, idx
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss, _g_idx):
+        z, E, idx = ctx.saved_tensors
+        depth, beta, residual = ctx.cfg
+        if g_out is not None:
+            g_out = g_out.contiguous()
+        if g_loss is not None:
+            g_loss = g_loss.contiguous()
+        gz, gE = ops.vq_bwd(z, E, idx, g_out, g_loss, residual, beta)
+        return gz, gE, None, None, None

@@ -202,3 +202,14 @@ def round_tf32(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
         out = torch.empty_like(x)
     _lib.check(_lib.lib().b200vq_round_tf32(_p(x), _p(out), x.numel(), _stream()), "round_tf32")
     return out
+
+
+def add_rows_mod(x: Tensor, table: Tensor) -> Tensor:
+    """x [M, D] + table[m % R] (R = table rows)"""
+    _req(x, "x"); _req(table, "table")
+    D = x.shape[-1]
+    M = x.numel() // D
+    R = table.numel() // D
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().b200vq_add_rows_mod(_p(x), _p(table), _p(out), M, D, R, _stream()), "add_rows_mod")
+    return out

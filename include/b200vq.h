@@ -99,6 +99,9 @@ int b200vq_colsum(const float* X, long long ld, int M, int N, float* out, void* 
 /* out = tf32-rounded copy of in (weights shadow for the tensor-core path) */
 int b200vq_round_tf32(const float* in, float* out, long long n, void* stream);
 
+/* out[m,:] = x[m,:] + table[m % R,:]  (token + de_pos_embedding, layers.py:210) */
+int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -214,6 +214,154 @@ def g_rowwise():
     print(f"colsum perf: {ms:.3f} ms {M*D*4/ms/1e6:.0f} GB/s")
 
 
+def g_attention():
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    torch.manual_seed(0)
+    for (B, N, heads, dh) in [(2, 16, 2, 32), (1, 24, 3, 64), (2, 200, 2, 64), (2, 1024, 4, 64), (1, 130, 1, 32)]:
+        inner = heads * dh
+        qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
+        scale = dh ** -0.5
+        o, lse = ops.attention_fwd(qkv, B, N, heads, dh, scale, False)
+        q, k, v = (t.reshape(B, N, heads, dh).permute(0, 2, 1, 3).double() for t in qkv.split(inner, dim=-1))
+        q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+        s = (q @ k.transpose(-1, -2)) * scale
+        p = torch.softmax(s, -1)
+        oref = (p @ v).permute(0, 2, 1, 3).reshape(B * N, inner)
+        lref = torch.logsumexp(s, -1).reshape(-1)
+        do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
+        oref.backward(do.double())
+        dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, False)
+        dref = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(B * N, inner) for t in (q, k, v)], dim=-1)
+        print(f"attn B={B} N={N} h={heads} dh={dh}: o {relerr(o.double(), oref.detach()):.2e} lse {relerr(lse.double(), lref.detach()):.2e} "
+              f"dq {relerr(dqkv[:, :inner].double(), dref[:, :inner]):.2e} dk {relerr(dqkv[:, inner:2*inner].double(), dref[:, inner:2*inner]):.2e} "
+              f"dv {relerr(dqkv[:, 2*inner:].double(), dref[:, 2*inner:]):.2e}", flush=True)
+    B, N, heads, dh = 64, 1024, 12, 64
+    inner = heads * dh
+    qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
+    ms = time_ms(lambda: ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True), iters=5, warm=2)
+    fl = 4 * B * heads * N * N * dh
+    print(f"attn fwd perf B={B}: {ms:.3f} ms {fl/ms/1e9:.1f} TFLOP/s")
+    o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
+    do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
+    ms = time_ms(lambda: ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True), iters=5, warm=2)
+    print(f"attn bwd perf B={B}: {ms:.3f} ms {2.5*fl/ms/1e9:.1f} TFLOP/s (5 GEMM-units counted)")
+
+
+def _load_modules(cfg, sd, device="cuda"):
+    import torch
+    import enhancing_transformers_b200 as etb
+    e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
+    enc = etb.ViTEncoder(cfg["image_size"], cfg["patch_size"], **e)
+    dec = etb.ViTDecoder(cfg["image_size"], cfg["patch_size"], **d)
+    vq = etb.VectorQuantizer(**q)
+    pre = torch.nn.Linear(e["dim"], q["embed_dim"]); post = torch.nn.Linear(q["embed_dim"], d["dim"])
+    for pfx, m in (("encoder.", enc), ("decoder.", dec), ("quantizer.", vq), ("pre_quant.", pre), ("post_quant.", post)):
+        m.load_state_dict({k[len(pfx):]: v for k, v in sd.items() if k.startswith(pfx)}, strict=True)
+        m.to(device)
+    return enc, dec, vq, pre, post
+
+
+def _step(mods, img):
+    enc, dec, vq, pre, post = mods
+    h = enc(img)
+    z = pre(h)
+    zq, qloss, idx = vq(z)
+    rec = dec(post(zq))
+    loss = ((rec - img) ** 2).mean() + qloss
+    return loss, rec, idx, h, z
+
+
+def g_model_tiny():
+    import numpy as np
+    import torch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vit_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    cfg = dict(image_size=32, patch_size=8, encoder=dict(dim=64, depth=2, heads=2, mlp_dim=128),
+               decoder=dict(dim=96, depth=2, heads=3, mlp_dim=160, dim_head=32), quantizer=dict(embed_dim=32, n_embed=256))
+    mods = _load_modules(cfg, sd)
+    img = torch.from_numpy(g["img"]).cuda()
+    loss, rec, idx, h, z = _step(mods, img)
+    print("tiny: enc", relerr(h.cpu(), torch.from_numpy(g["enc_out"])), "z", relerr(z.cpu(), torch.from_numpy(g["z"])),
+          "idx mismatch", int((idx.cpu().numpy() != g["idx"]).sum()), "rec", relerr(rec.cpu(), torch.from_numpy(g["rec"])),
+          "loss", loss.item(), float(g["loss"]))
+    loss.backward()
+    names = dict(encoder=mods[0], decoder=mods[1], quantizer=mods[2], pre_quant=mods[3], post_quant=mods[4])
+    worst = 0
+    for k in g.files:
+        if k.startswith("grad."):
+            mod, _, pname = k[5:].partition(".")
+            p = dict(names[mod].named_parameters())[pname]
+            e = relerr(p.grad.cpu(), torch.from_numpy(g[k]))
+            worst = max(worst, e)
+            if e > 3e-3:
+                print("   grad", k, e)
+    print("tiny: worst grad relerr", worst)
+
+
+def g_model_small():
+    import torch
+    from oracle import vitvq_oracle as O
+    import enhancing_transformers_b200 as etb
+    for name, B in (("small", 2), ("base", 1)):
+        cfg = O.CONFIGS[name]
+        sd = O.init_vitvq_sd(cfg, seed=0)
+        torch.manual_seed(0)
+        img = torch.rand(B, 3, 256, 256)
+        sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "pos_embedding" not in k) for k, v in sd.items()}
+        torch.set_num_threads(os.cpu_count())
+        t0 = time.time()
+        loss_ref, rec_ref, idx_ref = O.vitvq_loss(sdg, img, cfg)
+        loss_ref.backward()
+        print(f"{name}: oracle fwd+bwd B={B} took {time.time()-t0:.1f}s on {os.cpu_count()} threads")
+        mods = _load_modules(cfg, sd)
+        loss, rec, idx, h, z = _step(mods, img.cuda())
+        loss.backward()
+        agree = (idx.cpu() == idx_ref).float().mean().item()
+        print(f"{name}: loss {loss.item():.6f} ref {loss_ref.item():.6f}; rec maxabs-rel {relerr(rec.cpu(), rec_ref.detach()):.3e} "
+              f"rel-l2 {((rec.cpu()-rec_ref.detach()).norm()/rec_ref.detach().norm()).item():.3e}; idx agree {agree:.5f}")
+        names = dict(encoder=mods[0], decoder=mods[1], quantizer=mods[2], pre_quant=mods[3], post_quant=mods[4])
+        worst = []
+        for k, v in sdg.items():
+            if v.grad is None:
+                continue
+            mod, _, pname = k.partition(".")
+            p = dict(names[mod].named_parameters())[pname]
+            worst.append((((p.grad.cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-30)).item(), k))
+        worst.sort(reverse=True)
+        print("   worst grad rel-l2:", [(f"{e:.2e}", k) for e, k in worst[:5]])
+        del mods
+        etb.functional.clear_shadow_cache()
+        torch.cuda.empty_cache()
+
+
+def g_model_perf():
+    import torch
+    from oracle import vitvq_oracle as O
+    import enhancing_transformers_b200 as etb
+    cfg = O.CONFIGS["base"]
+    sd = O.init_vitvq_sd(cfg, seed=0)
+    mods = _load_modules(cfg, sd)
+    for cg in (1, 2):
+        etb.functional.GEMM_CTA_GROUP = cg
+        for B in (16, 64, 128):
+            img = torch.rand(B, 3, 256, 256, device="cuda")
+
+            def step():
+                for m in mods:
+                    m.zero_grad(set_to_none=True)
+                loss = _step(mods, img)[0]
+                loss.backward()
+            try:
+                ms = time_ms(step, iters=3, warm=2)
+                fl = 3 * O.flops_per_image(cfg) * B
+                print(f"base fwd+bwd cg={cg} B={B}: {ms:.1f} ms  {B/ms*1e3:.1f} img/s  {fl/ms/1e9:.1f} TFLOP/s  mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
+            except Exception as ex:
+                print(f"base B={B} cg={cg} failed: {ex}")
+                break
+
+
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
 
 if __name__ == "__main__":
