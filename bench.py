@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the ViT-VQGAN fwd+bwd hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 5 --warmup 3
+    python bench.py --impl reference --steps 2 --warmup 1      # the CPU arm (oracle port)
+
+One "step" = x -> ViTEncoder -> pre_quant -> VectorQuantizer -> post_quant -> ViTDecoder ->
+loss = mean((rec-x)^2) + qloss -> backward, fp32 parameters, no optimizer step (SURVEY.md
+section 8d).  Workload: imagenet_vitvq_base.yaml shapes, synthetic 256x256 images, batch 128
+per GPU (BASELINE.json configs[1]); weak scaling, gradients all-reduced by NCCL (DDP).
+
+Prints ONE JSON line on rank 0 (see DESIGN.md 'Measurement' for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (256x256) ViT-VQGAN fwd+bwd"
+UNIT = "images/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = max((float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "power_w_max": pw}
+
+
+def oracle_step(cfg_name, batch, threads):
+    """one fwd+bwd of the CPU oracle (the port of the reference's PyTorch path); returns seconds"""
+    import torch
+    from oracle import vitvq_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.CONFIGS[cfg_name]
+    sd = O.init_vitvq_sd(cfg, seed=0)
+    sd = {k: v.requires_grad_(v.is_floating_point() and "pos_embedding" not in k) for k, v in sd.items()}
+    img = torch.rand(batch, 3, cfg["image_size"], cfg["image_size"], generator=torch.Generator().manual_seed(0))
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss, _, _ = O.vitvq_loss(sd, img, cfg)
+        loss.backward()
+        return time.perf_counter() - t0
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  /root/reference (Python, needs
+    pytorch_lightning to import as a package) cannot travel to the GPU box, so this times
+    oracle/vitvq_oracle.py, the line-by-line functional port pinned against the reference's
+    outputs (kind = "port"), with every host thread, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = args.ref_batch
+    step = oracle_step(args.config, sample_b, threads)
+    for _ in range(max(1, args.warmup) if args.warmup else 0):
+        step()
+    times = [step() for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    val = sample_b / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes, synthetic 256x256, fwd+bwd, CPU sample of {sample_b} images/step",
+                   "global_batch": sample_b, "parallelism": "host threads"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} fwd+bwd steps of {sample_b} images, {args.config} config, torch CPU fp32"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="base", choices=["small", "base", "base_rq4", "large"])
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--cta-group", type=int, default=int(os.environ.get("B200VQ_CTA_GROUP", "1")))
+    ap.add_argument("--ref-batch", type=int, default=4, help="images per CPU step for --impl reference / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    import enhancing_transformers_b200 as etb
+    from oracle import vitvq_oracle as O   # FLOP model + config table + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    etb.functional.GEMM_CTA_GROUP = args.cta_group
+
+    cfg = O.CONFIGS[args.config]
+    e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
+
+    class HotPath(nn.Module):
+        """the five modules of ViTVQ.forward (vitvqgan.py:35-39,44-72) + the bench loss"""
+
+        def __init__(self):
+            super().__init__()
+            self.encoder = etb.ViTEncoder(cfg["image_size"], cfg["patch_size"], **e)
+            self.decoder = etb.ViTDecoder(cfg["image_size"], cfg["patch_size"], **d)
+            self.quantizer = etb.VectorQuantizer(**q)
+            self.pre_quant = nn.Linear(e["dim"], q["embed_dim"])
+            self.post_quant = nn.Linear(q["embed_dim"], d["dim"])
+
+        def forward(self, x):
+            quant, qloss, _ = self.quantizer(self.pre_quant(self.encoder(x)))
+            rec = self.decoder(self.post_quant(quant))
+            return ((rec - x) ** 2).mean() + qloss
+
+    torch.manual_seed(0)
+    model = HotPath().to(dev)
+    net = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    B = args.batch
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_imgs = torch.rand(B, 3, cfg["image_size"], cfg["image_size"], generator=gen).pin_memory()
+    dev_imgs = host_imgs.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def step(x):
+        for p in model.parameters():
+            p.grad = None
+        loss = net(x)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -----------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(dev_imgs)
+    barrier()
+
+    # ---- device-resident timed region (value) + per-GEMM events (roofline) -------------------
+    gemm_events = []
+    orig_gemm = etb.ops.gemm
+
+    def timed_gemm(a, b, M, N, K, **kw):
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig_gemm(a, b, M, N, K, **kw)
+        t.record()
+        gemm_events.append((s, t, 2.0 * M * N * K * kw.get("splits", 1)))
+        return out
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    etb.ops.gemm = timed_gemm
+    etb.functional.ops.gemm = timed_gemm
+    launches0 = etb.ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(dev_imgs)
+    ev1.record()
+    barrier()
+    launches = etb.ops.launch_count() - launches0
+    etb.ops.gemm = orig_gemm
+    etb.functional.ops.gemm = orig_gemm
+    ms_total = ev0.elapsed_time(ev1)
+    gemm_ms = sum(s.elapsed_time(t) for s, t, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    n_gemm = len(gemm_events)
+
+    # ---- end-to-end timed region: pinned host images in, loss out, every step ------------------
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    last = 0.0
+    for _ in range(args.steps):
+        x = host_imgs.to(dev, non_blocking=True)
+        last = float(step(x).item())      # device -> host read of the step's result
+    ev3.record()
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        imgs = world * B * args.steps
+        value = imgs / (ms_total / 1e3)
+        e2e = imgs / (ms_e2e / 1e3)
+        flops_step = 3.0 * O.flops_per_image(cfg) * B
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes (ViT-VQGAN-{args.config}), synthetic 256x256x3, "
+                                   f"fwd+bwd, batch {B}/GPU", "global_batch": world * B, "per_gpu_batch": B,
+                       "parallelism": f"dp{world}", "l2_hygiene": "inputs_exceed_l2 (activations >> 126 MB per step)",
+                       "gemm_cta_group": args.cta_group, "precision": "tf32 tensor-core GEMM/attention (rn-rounded operands, fp32 accumulate); fp32 VQ/LayerNorm"},
+            "model_tflops_per_gpu": flops_step / (ms_total / args.steps / 1e3) / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peaks["source"] + ": cuBLAS bf16 sustained; tf32 issues at half the bf16 rate, so frac <= ~0.5 by construction",
+                         "frac_of_half_rate_peak": achieved / (peak / 2), "launches_timed": n_gemm,
+                         "share_of_step": gemm_ms / ms_total, "hbm_peak_gbs": peaks["hbm_gbs"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cstep = oracle_step(args.config, args.ref_batch, threads)
+            sec = cstep()
+            line["cpu_baseline"] = {"value": args.ref_batch / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"1 fwd+bwd step of {args.ref_batch} images, {args.config} config, oracle port on torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -80,7 +80,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CG);   // CG producers arrive (the follower arrives remotely)
+      mbar_init(&full_bar[s], 1);    // the leader's producer arrives once, expecting the bytes of the whole pair
       mbar_init(&empty_bar[s], 1);   // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -124,8 +124,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (BMAJ == 0) tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
             else                     tma_load_3d(sb, &tmB, &full_bar[stage], 0, k0, n0 / 32);
           } else {
+            // Only the leader arrives (expecting both CTAs' bytes).  The follower's TMA credits
+            // the leader's barrier directly; it may land before the leader's expect_tx of the
+            // same phase (tx-count goes transiently negative), which is legal: the phase cannot
+            // complete before the leader's single pending arrival.
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            else        mbar_arrive_remote(&full_bar[stage], 0);
             if constexpr (AMAJ == 0) tma_load_2d_2sm(sa, &tmA, &full_bar[stage], k0, m0);
             else                     tma_load_3d_2sm(sa, &tmA, &full_bar[stage], 0, k0, m0 / 32);
             if constexpr (BMAJ == 0) tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, n0);

@@ -1,0 +1,145 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/b200vq.h declares, the nn.Module surface matches the reference's constructor /
+state-dict contract, and the product path refuses to run on CPU."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import enhancing_transformers_b200 as etb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200vq.h")).read()
+    declared = set(re.findall(r"\b(b200vq_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = etb._lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in b200vq.h but not exported by libb200vq.so"
+    assert declared == set(etb._lib.EXPORTS), declared ^ set(etb._lib.EXPORTS)
+    assert lib.b200vq_version() == 100
+    assert lib.b200vq_arch() == b"sm_100a"
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    enc = etb.ViTEncoder(image_size=32, patch_size=8, dim=64, depth=1, heads=2, mlp_dim=64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.rand(1, 3, 32, 32))
+    vq = etb.VectorQuantizer(embed_dim=32, n_embed=64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq(torch.randn(1, 4, 32))
+    with pytest.raises(NotImplementedError):
+        etb.VectorQuantizer(embed_dim=32, n_embed=64, use_norm=False)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from enhancing_transformers_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_constructor_signatures_match_reference():
+    # reference layers.py:154-155,186-187 and quantizers.py:67-68 (keyword names are API: YAML dicts are splatted)
+    for cls in (etb.ViTEncoder, etb.ViTDecoder):
+        params = list(inspect.signature(cls.__init__).parameters)
+        assert params == ["self", "image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "channels", "dim_head"]
+        sig = inspect.signature(cls.__init__)
+        assert sig.parameters["channels"].default == 3 and sig.parameters["dim_head"].default == 64
+    sig = inspect.signature(etb.VectorQuantizer.__init__)
+    assert list(sig.parameters) == ["self", "embed_dim", "n_embed", "beta", "use_norm", "use_residual", "num_quantizers", "kwargs"]
+    assert sig.parameters["beta"].default == 0.25 and sig.parameters["use_norm"].default is True
+
+
+def test_state_dict_keys_and_shapes_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    ref = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
+    enc = etb.ViTEncoder(image_size=32, patch_size=8, dim=64, depth=2, heads=2, mlp_dim=128)
+    dec = etb.ViTDecoder(image_size=32, patch_size=8, dim=96, depth=2, heads=3, mlp_dim=160, dim_head=32)
+    vq = etb.VectorQuantizer(embed_dim=32, n_embed=256)
+    for pfx, mod in (("encoder.", enc), ("decoder.", dec), ("quantizer.", vq)):
+        mine = {pfx + k: tuple(v.shape) for k, v in mod.state_dict().items()}
+        theirs = {k: tuple(v.shape) for k, v in ref.items() if k.startswith(pfx)}
+        assert mine == theirs
+        mod.load_state_dict({k[len(pfx):]: torch.from_numpy(v) for k, v in ref.items() if k.startswith(pfx)}, strict=True)
+    # the positional tables are rebuilt bit-exactly and are frozen parameters inside the state dict
+    np.testing.assert_array_equal(etb.ViTEncoder(32, 8, 64, 1, 2, 64).en_pos_embedding.numpy(), ref["encoder.en_pos_embedding"])
+    assert not enc.en_pos_embedding.requires_grad and not dec.de_pos_embedding.requires_grad
+    assert dec.get_last_layer() is dec.to_pixel[-1].weight
+    assert enc.num_patches == 16 and enc.patch_dim == 192
+
+
+def test_quantizer_attributes_read_by_lightning_module():
+    vq = etb.VectorQuantizer(embed_dim=32, n_embed=64, use_residual=True, num_quantizers=4)
+    assert vq.use_residual is True and vq.num_quantizers == 4 and vq.straight_through is True
+    code = torch.tensor([[1, 2, 3, 4]])
+    q = vq.norm(vq.embedding(code))              # vitvqgan.py:82-83 on CPU tensors still works (plain torch)
+    assert q.shape == (1, 4, 32)
+    torch.testing.assert_close(q.norm(dim=-1), torch.ones(1, 4))
+
+
+def test_init_distributions_follow_reference():
+    torch.manual_seed(0)
+    enc = etb.ViTEncoder(image_size=64, patch_size=8, dim=256, depth=1, heads=4, mlp_dim=512)
+    lin = enc.transformer.layers[0][1].fn.net[0]
+    bound = (6.0 / (256 + 512)) ** 0.5
+    assert lin.weight.abs().max() <= bound and lin.weight.abs().max() > 0.9 * bound
+    assert torch.count_nonzero(lin.bias) == 0
+    ln = enc.transformer.norm
+    assert torch.all(ln.weight == 1) and torch.all(ln.bias == 0)
+    w = enc.to_patch_embedding[0].weight
+    assert w.abs().max() <= (6.0 / (256 + 192)) ** 0.5
+    vq = etb.VectorQuantizer(32, 4096)
+    assert abs(vq.embedding.weight.std().item() - 1.0) < 0.05
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_unchanged_lightning_module_constructs_with_patched_classes(monkeypatch):
+    """ViTVQ from the reference's vitvqgan.py, unedited, built on top of the replacement classes
+    (stub pytorch_lightning / omegaconf, which are not installed here)."""
+    import importlib.util
+    import sys
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, m)
+        return m
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    stub("omegaconf", OmegaConf=AttrDict)
+    pl = stub("pytorch_lightning", LightningModule=torch.nn.Module)
+    for pkg in ("enhancing", "enhancing.modules", "enhancing.modules.stage1", "enhancing.utils"):
+        stub(pkg).__path__ = []
+    stub("enhancing.utils.general", initialize_from_config=lambda cfg: torch.nn.Identity())
+    etb.install_as_reference_modules()
+    for n in ("enhancing.modules.stage1.layers", "enhancing.modules.stage1.quantizers"):
+        monkeypatch.setitem(sys.modules, n, sys.modules[n])
+    spec = importlib.util.spec_from_file_location("enhancing.modules.stage1.vitvqgan",
+                                                  os.path.join(REF, "enhancing", "modules", "stage1", "vitvqgan.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, spec.name, mod)
+    spec.loader.exec_module(mod)
+    assert mod.Encoder is etb.ViTEncoder and mod.Decoder is etb.ViTDecoder and mod.VectorQuantizer is etb.VectorQuantizer
+    enc = AttrDict(dim=64, depth=1, heads=2, mlp_dim=64)
+    model = mod.ViTVQ(image_key="image", image_size=32, patch_size=8, encoder=enc, decoder=enc,
+                      quantizer=AttrDict(embed_dim=32, n_embed=128), loss=AttrDict())
+    assert isinstance(model.encoder, etb.ViTEncoder) and isinstance(model.quantizer, etb.VectorQuantizer)
+    keys = set(model.state_dict())
+    assert {"encoder.en_pos_embedding", "decoder.to_pixel.1.weight", "quantizer.embedding.weight", "pre_quant.weight"} <= keys
+    # patch() on an already-imported module rebinds the same three names
+    mod.Encoder = None
+    etb.patch(mod)
+    assert mod.Encoder is etb.ViTEncoder

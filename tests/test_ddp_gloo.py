@@ -1,0 +1,74 @@
+"""world_size-2 gloo test of the multi-GPU host logic: images are
+sharded evenly across ranks, every rank takes the *per-rank* mean loss, and the gradient
+all-reduce(mean) reproduces the single-process gradient on the concatenated batch -- including
+the dense codebook gradient.  The oracle stands in for the CUDA modules (no GPU here); on the GPU
+the same wiring runs through bench.py's DistributedDataParallel wrapper."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(image_size=32, patch_size=8, encoder=dict(dim=32, depth=1, heads=1, mlp_dim=32, dim_head=32),
+           decoder=dict(dim=32, depth=1, heads=1, mlp_dim=32, dim_head=32), quantizer=dict(embed_dim=32, n_embed=64))
+
+
+class OracleNet(torch.nn.Module):
+    def __init__(self, sd):
+        super().__init__()
+        self.names = list(sd)
+        self.params = torch.nn.ParameterList([torch.nn.Parameter(v.clone(), requires_grad="pos_embedding" not in k)
+                                              for k, v in sd.items()])
+
+    def forward(self, img):
+        from oracle import vitvq_oracle as O
+        sd = dict(zip(self.names, self.params))
+        return O.vitvq_loss(sd, img, CFG)[0]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import vitvq_oracle as O
+    torch.set_num_threads(1)
+    sd = O.init_vitvq_sd(CFG, seed=0)
+    imgs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    net = torch.nn.parallel.DistributedDataParallel(OracleNet(sd))
+    shard = imgs[rank * 2:(rank + 1) * 2]                       # even split, as main.py's DDP does
+    net(shard).backward()
+    grads = {n: p.grad.clone() for n, p in zip(net.module.names, net.module.params) if p.grad is not None}
+    if rank == 0:
+        single = OracleNet(sd)
+        single(imgs).backward()
+        worst = 0.0
+        for n, p in zip(single.names, single.params):
+            if p.grad is None:
+                continue
+            err = (grads[n] - p.grad).abs().max().item() / (p.grad.abs().max().item() + 1e-30)
+            worst = max(worst, err)
+        q.put(worst)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_ddp_gradients_equal_single_process():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    worst = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert worst < 1e-4, worst

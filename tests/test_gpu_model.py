@@ -1,0 +1,138 @@
+"""GPU parity of the nn.Module boundary: the replacement ViTEncoder / ViTDecoder /
+VectorQuantizer, wired as ViTVQ.forward wires them (vitvqgan.py:44-72), against the reference's
+own outputs (golden fixtures) and against the oracle sharing one state_dict.
+Tolerance: north_star's 1e-3 relative (of the tensor's max) for reconstructions, codes bit-exact
+on identical z."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import enhancing_transformers_b200 as etb
+from oracle import vitvq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def build(cfg, sd):
+    e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
+    mods = dict(encoder=etb.ViTEncoder(cfg["image_size"], cfg["patch_size"], **e),
+                decoder=etb.ViTDecoder(cfg["image_size"], cfg["patch_size"], **d),
+                quantizer=etb.VectorQuantizer(**q),
+                pre_quant=torch.nn.Linear(e["dim"], q["embed_dim"]), post_quant=torch.nn.Linear(q["embed_dim"], d["dim"]))
+    for name, m in mods.items():
+        m.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=True)
+        m.cuda()
+    return mods
+
+
+def run(mods, img):
+    h = mods["encoder"](img)
+    z = mods["pre_quant"](h)
+    zq, qloss, idx = mods["quantizer"](z)
+    rec = mods["decoder"](mods["post_quant"](zq))
+    return ((rec - img) ** 2).mean() + qloss, rec, idx, h, z
+
+
+GOLD_CFG = dict(image_size=32, patch_size=8, encoder=dict(dim=64, depth=2, heads=2, mlp_dim=128),
+                decoder=dict(dim=96, depth=2, heads=3, mlp_dim=160, dim_head=32), quantizer=dict(embed_dim=32, n_embed=256))
+
+
+def test_against_reference_golden_fwd_bwd(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    mods = build(GOLD_CFG, sd)
+    loss, rec, idx, h, z = run(mods, torch.from_numpy(g["img"]).cuda())
+    assert relmax(h.cpu(), torch.from_numpy(g["enc_out"])) < 1e-3
+    # codes: bit-exact on identical z; end to end they inherit the encoder's tf32 rounding, so audit near-ties
+    same = O.vq_forward(z.detach().cpu(), sd["quantizer.embedding.weight"])[2]
+    assert torch.equal(idx.cpu(), same)
+    if not np.array_equal(idx.cpu().numpy(), g["idx"]):
+        bad = np.nonzero(idx.cpu().numpy().reshape(-1) != g["idx"].reshape(-1))[0]
+        gaps = O.vq_top2_gap_f64(g["z"].reshape(-1, 32)[bad], g["sd.quantizer.embedding.weight"])
+        assert (gaps < 1e-2).all(), gaps
+    else:
+        assert relmax(rec.cpu(), torch.from_numpy(g["rec"])) < 1e-3
+        assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad."):
+            mod, _, pname = k[5:].partition(".")
+            p = dict(mods[mod].named_parameters())[pname]
+            ref = torch.from_numpy(g[k])
+            rel = ((p.grad.cpu() - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+            assert rel < 5e-3, (k, rel)
+    # decode_codes path (vitvqgan.py:81-90) incl. the fused embed helper
+    with torch.no_grad():
+        q = mods["quantizer"].embed_codes(torch.from_numpy(g["idx"]).cuda())
+        d = mods["decoder"](mods["post_quant"](q))
+        assert relmax(d.cpu(), torch.from_numpy(g["decode_codes"])) < 1e-3
+        q2 = mods["quantizer"].norm(mods["quantizer"].embedding(torch.from_numpy(g["idx"]).cuda()))
+        assert torch.allclose(q, q2, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 3), ("small", 1)])
+def test_against_oracle_shared_state_dict(name, B):
+    cfg = O.CONFIGS[name]
+    sd = O.init_vitvq_sd(cfg, seed=1)
+    img = torch.rand(B, 3, cfg["image_size"], cfg["image_size"], generator=torch.Generator().manual_seed(2))
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "pos_embedding" not in k) for k, v in sd.items()}
+    loss_ref, rec_ref, idx_ref = O.vitvq_loss(sdg, img, cfg)
+    loss_ref.backward()
+    mods = build(cfg, sd)
+    loss, rec, idx, h, z = run(mods, img.cuda())
+    loss.backward()
+    assert torch.equal(idx.cpu(), O.vq_forward(z.detach().cpu(), sd["quantizer.embedding.weight"])[2])
+    agree = (idx.cpu() == idx_ref).float().mean().item()
+    assert agree > 0.995, agree
+    if agree == 1.0:
+        assert relmax(rec.cpu(), rec_ref.detach()) < 1e-3
+        assert abs(loss.item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())
+    for k, v in sdg.items():
+        if v.grad is None or v.grad.norm() == 0:
+            continue
+        mod, _, pname = k.partition(".")
+        p = dict(mods[mod].named_parameters())[pname]
+        rel = ((p.grad.cpu() - v.grad).norm() / v.grad.norm()).item()
+        assert rel < (2e-2 if agree < 1.0 else 5e-3), (k, rel)
+
+
+def test_residual_quantizer_module_and_modes():
+    """use_residual=True, num_quantizers=4 (BASELINE config 3) + eval/no_grad + double forward"""
+    torch.manual_seed(0)
+    vq = etb.VectorQuantizer(embed_dim=32, n_embed=512, use_residual=True, num_quantizers=4).cuda()
+    z = torch.randn(2, 64, 32, device="cuda", requires_grad=True)
+    zq, loss, idx = vq(z)
+    assert idx.shape == (2, 64, 4) and idx.dtype == torch.int64
+    ref = O.vq_forward(z.detach().cpu().requires_grad_(True), vq.embedding.weight.detach().cpu().requires_grad_(True), 0.25, True, 4)
+    assert torch.equal(idx.cpu(), ref[2])
+    assert torch.allclose(zq.detach().cpu(), ref[0].detach(), atol=1e-6)
+    (zq.sum() + loss).backward()
+    assert torch.allclose(z.grad, torch.ones_like(z))          # residual mode: z only gets the straight-through gradient
+    vq.eval()
+    with torch.no_grad():
+        zq2, loss2, idx2 = vq(z)
+        assert torch.equal(idx2, idx)
+        q = vq.embed_codes(idx)
+        assert torch.allclose(q, zq2, atol=1e-5)
+
+
+def test_sub_modules_run_standalone():
+    torch.manual_seed(0)
+    attn = etb.Attention(64, heads=2, dim_head=32).cuda()
+    ff = etb.PreNorm(64, etb.FeedForward(64, 96)).cuda()
+    x = torch.randn(2, 24, 64, device="cuda", requires_grad=True)
+    y = ff(attn(x))
+    xr = x.detach().cpu().requires_grad_(True)
+    sd = {k: v.detach().cpu() for k, v in list(attn.state_dict().items()) + list(ff.state_dict().items())}
+    a = O.attention(xr, sd["to_qkv.weight"], sd["to_out.weight"], sd["to_out.bias"], 2)
+    yr = O.feed_forward(O.layer_norm(a, sd["norm.weight"], sd["norm.bias"]), sd["fn.net.0.weight"], sd["fn.net.0.bias"],
+                        sd["fn.net.2.weight"], sd["fn.net.2.bias"])
+    assert relmax(y.detach().cpu(), yr.detach()) < 2e-3
+    y.sum().backward(); yr.sum().backward()
+    assert relmax(x.grad.cpu(), xr.grad) < 5e-3
