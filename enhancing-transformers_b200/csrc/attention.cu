@@ -11,6 +11,8 @@
 // (dK, dV) and one CTA per query tile (dQ).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -411,9 +413,19 @@ static int attn_fwd_launch(const float* qkv, float* out, float* lse, int B, int 
   return 0;
 }
 
+int attention_forward_tc(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+
+// B200VQ_ATTN_FWD=mma selects the v1 mma.sync kernel (kept for A/B measurements); default is tcgen05
+static bool use_mma_fwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200VQ_ATTN_FWD"); v = (e && e[0] == 'm') ? 1 : 0; }
+  return v == 1;
+}
+
 int attention_forward(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale, int round_out,
                       cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  if (!use_mma_fwd()) return attention_forward_tc(qkv, out, lse, B, N, heads, dh, scale, round_out, stream);
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
   if (dh == 64) return attn_fwd_launch<64>(qkv, out, lse, B, N, heads, scale, round_out, stream);

@@ -32,11 +32,10 @@ struct GemmParams {
   float* C;
   long long ldc, c_split_stride;
   const float* bias;           // [N] or null
-  const float* res;            // residual added in the epilogue, or null
+  const float* res;            // residual added in the epilogue through direct loads (row % res_row_mod), or null
   long long ldres;
   int res_row_mod;             // >0: residual row = row % res_row_mod (positional table)
-  const float* aux;            // tanh'(.) multiplier source: out *= 1 - aux^2, or null
-  long long ldaux;
+  int in_mode;                 // 0 none, 1: + tile of tmIn (residual), 2: * (1 - tile^2) (tanh backward)
   int act;                     // 0 none, 1 tanh
   int round_out;               // 1: round the stored value to tf32 (it only feeds another GEMM)
 };
@@ -51,25 +50,31 @@ struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 4;
   static constexpr int B_BYTES = BN_CTA * kBK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int STAGING_BYTES = 4 * 16384;     // per epilogue warp: out[2][4 KB] + in[2][4 KB]
+  static constexpr int MAX_SMEM = 232448;             // 227 KB opt-in limit
+  static constexpr int RING_BUDGET = MAX_SMEM - STAGING_BYTES - 1024 - 512;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 template <int BN, int CG, int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* in_full_all = bars + 2 * STAGES + 4;  // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,6 +84,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.in_mode) tma_prefetch_desc(&tmIn);
+    for (int i = 0; i < 8; ++i) mbar_init(&in_full_all[i], 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);    // the leader's producer arrives once, expecting the bytes of the whole pair
       mbar_init(&empty_bar[s], 1);   // one tcgen05.commit
@@ -177,53 +185,89 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps
+    // Each warp owns 32 rows of the tile (TMEM lane quarter q).  Per 32-column chunk: tcgen05.ld ->
+    // registers -> fused math -> 128B-swizzled smem box -> TMA store (fully coalesced, clipped at the
+    // matrix edge).  Residual / tanh' inputs arrive the same way through TMA loads, one chunk ahead.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int ew = warp - 2;
+    uint8_t* out_buf = staging + ew * 16384;
+    uint8_t* in_buf = out_buf + 8192;
+    uint64_t* in_full = in_full_all + ew * 2;
+    const uint32_t swz = lane & 7;
+    const bool tma_in = p.in_mode != 0;
+    uint32_t in_issue = 0, in_use = 0, out_cnt = 0;
+    constexpr int NCHUNK = BN / 32;
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int z = t / tiles_per_split;
       const int r = t - z * tiles_per_split;
       const int mb = r / p.num_n_blocks, nb = r - mb * p.num_n_blocks;
-      const int row = (mb * CG + (int)cta_rank) * kBM + q * 32 + lane;
+      const int row0 = (mb * CG + (int)cta_rank) * kBM + q * 32;
+      const int row = row0 + lane;
       const int n0 = nb * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (tma_in && lane == 0) {   // first input chunk of this tile (its buffer was released by the previous tile)
+        mbar_arrive_expect_tx(&in_full[in_issue & 1], 4096);
+        tma_load_2d(in_buf + (in_issue & 1) * 4096, &tmIn, &in_full[in_issue & 1], n0, row0);
+      }
+      if (tma_in) ++in_issue;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const bool row_ok = row < p.M;
-      float* crow = p.C + (long long)z * p.c_split_stride + (long long)row * p.ldc;
       const float* rrow = nullptr;
-      if (p.res) rrow = p.res + (long long)(p.res_row_mod > 0 ? row % p.res_row_mod : row) * p.ldres;
-      const float* arow = p.aux ? p.aux + (long long)row * p.ldaux : nullptr;
+      if (p.res && row < p.M) rrow = p.res + (long long)(p.res_row_mod > 0 ? row % p.res_row_mod : row) * p.ldres;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col0 = n0 + c * 32;
+        if (tma_in && c + 1 < NCHUNK) {
+          __syncwarp();            // every lane has finished reading the buffer about to be refilled
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&in_full[in_issue & 1], 4096);
+            tma_load_2d(in_buf + (in_issue & 1) * 4096, &tmIn, &in_full[in_issue & 1], col0 + 32, row0);
+          }
+          ++in_issue;
+        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE + c * 32, v);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
+        const uint8_t* inb = in_buf + (in_use & 1) * 4096 + lane * 128;
+        if (tma_in) { mbar_wait(&in_full[in_use & 1], (in_use >> 1) & 1); ++in_use; }
+        // the staging buffer we are about to overwrite must have been read by its TMA store
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* outb = out_buf + (out_cnt & 1) * 4096 + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-              if (arow) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(arow + col0 + j));
-                o.x *= 1.f - a.x * a.x; o.y *= 1.f - a.y * a.y; o.z *= 1.f - a.z * a.z; o.w *= 1.f - a.w * a.w;
-              }
-              if (rrow) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(rrow + col0 + j));
-                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-              }
-              if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              *reinterpret_cast<float4*>(crow + col0 + j) = o;
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          const int col = col0 + 4 * j;
+          if (p.bias && col < p.N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+          if (tma_in) {
+            const float4 a = *reinterpret_cast<const float4*>(inb + ((j ^ swz) << 4));
+            if (p.in_mode == 2) {
+              o.x *= 1.f - a.x * a.x; o.y *= 1.f - a.y * a.y; o.z *= 1.f - a.z * a.z; o.w *= 1.f - a.w * a.w;
+            } else {
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
             }
           }
+          if (rrow && col < p.N) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rrow + col));
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          *reinterpret_cast<float4*>(outb + ((j ^ swz) << 4)) = o;
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (col0 < p.N && row0 < p.M) tma_store_3d(&tmC, out_buf + (out_cnt & 1) * 4096, col0, row0, z);
+          bulk_commit_group();
+        }
+        ++out_cnt;
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -232,6 +276,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else                   mbar_arrive_remote(&tmem_empty[acc], 0);
       }
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // smem must outlive the last stores' reads
   }
 
   // ------------------------------------------------------------------ teardown
@@ -265,26 +310,33 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct TmapKey {
-  const void* ptr; long long ld; int rows, cols, major, box_mn;
+  const void* ptr; int rank, swz; unsigned long long dims[5], strides[4]; unsigned box[5];
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && major == o.major && box_mn == o.box_mn;
+    if (ptr != o.ptr || rank != o.rank || swz != o.swz) return false;
+    for (int i = 0; i < rank; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i + 1 < rank; ++i) if (strides[i] != o.strides[i]) return false;
+    return true;
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix((size_t)k.ld); mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.major); mix((size_t)k.box_mn);
+    mix((size_t)k.rank * 2 + k.swz);
+    for (int i = 0; i < k.rank; ++i) { mix((size_t)k.dims[i]); mix((size_t)k.box[i]); }
+    for (int i = 0; i + 1 < k.rank; ++i) mix((size_t)k.strides[i]);
     return h;
   }
 };
 
-// major 0: matrix [rows = MN extent, cols = K extent], box {32 k, box_mn rows}
-// major 1: matrix [rows = K extent, cols = MN extent], viewed as {32, rows, cols/32}, box {32, 32, box_mn/32}
-static int make_operand_tmap(CUtensorMap* out, const float* ptr, long long ld, int rows, int cols, int major, int box_mn) {
+int make_tensor_map_f32(CUtensorMap* out, const float* ptr, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, int swizzle_base32) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   static std::mutex mu;
-  TmapKey key{ptr, ld, rows, cols, major, box_mn};
+  TmapKey key{};
+  key.ptr = ptr; key.rank = rank; key.swz = swizzle_base32;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -292,35 +344,40 @@ static int make_operand_tmap(CUtensorMap* out, const float* ptr, long long ld, i
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(-4, "cuTensorMapEncodeTiled entry point not available");
-  CUresult r;
-  if (major == 0) {
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_mn};
-    cuuint32_t es[2] = {1, 1};
-    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-    cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
-    cuuint32_t es[3] = {1, 1, 1};
-    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_base32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error(-4, "cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d cols=%d major=%d box=%d", (int)r,
-                     ptr, ld, rows, cols, major, box_mn);
+    return set_error(-4, "cuTensorMapEncodeTiled failed (%d) ptr=%p rank=%d dims0=%llu box0=%u", (int)r, ptr, rank, dims[0], box[0]);
   std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 4096) cache.clear();
+  if (cache.size() > 8192) cache.clear();
   cache.emplace(key, *out);
   return 0;
 }
 
+// major 0: matrix [rows = MN extent, cols = K extent], box {32 k, box_mn rows}
+// major 1: matrix [rows = K extent, cols = MN extent], viewed as {32, rows, cols/32}, box {32, 32, box_mn/32}
+static int make_operand_tmap(CUtensorMap* out, const float* ptr, long long ld, int rows, int cols, int major, int box_mn) {
+  if (major == 0) {
+    const unsigned long long dims[2] = {(unsigned long long)cols, (unsigned long long)rows};
+    const unsigned long long strides[1] = {(unsigned long long)ld * 4};
+    const unsigned box[2] = {32, (unsigned)box_mn};
+    return make_tensor_map_f32(out, ptr, 2, dims, strides, box, 0);
+  }
+  const unsigned long long dims[3] = {32, (unsigned long long)rows, (unsigned long long)(cols / 32)};
+  const unsigned long long strides[2] = {(unsigned long long)ld * 4, 128};
+  const unsigned box[3] = {32, 32, (unsigned)(box_mn / 32)};
+  return make_tensor_map_f32(out, ptr, 3, dims, strides, box, 1);
+}
+
 template <int BN, int CG, int AMAJ, int BMAJ>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmIn,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   auto kern = gemm_tf32_kernel<BN, CG, AMAJ, BMAJ>;
   static bool configured = false;
@@ -352,17 +409,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   int clusters = max_clusters < total ? max_clusters : total;
   cfg.gridDim = dim3(clusters * CG);
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmIn, p));
   count_launch();
   return 0;
 }
 
 template <int BN, int CG>
-static int dispatch_major(int am, int bm, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
-  if (am == 0 && bm == 0) return launch_gemm<BN, CG, 0, 0>(a, b, p, s);
-  if (am == 0 && bm == 1) return launch_gemm<BN, CG, 0, 1>(a, b, p, s);
-  if (am == 1 && bm == 1) return launch_gemm<BN, CG, 1, 1>(a, b, p, s);
-  if (am == 1 && bm == 0) return launch_gemm<BN, CG, 1, 0>(a, b, p, s);
+static int dispatch_major(int am, int bm, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                          const CUtensorMap& in, const GemmParams& p, cudaStream_t s) {
+  if (am == 0 && bm == 0) return launch_gemm<BN, CG, 0, 0>(a, b, c, in, p, s);
+  if (am == 0 && bm == 1) return launch_gemm<BN, CG, 0, 1>(a, b, c, in, p, s);
+  if (am == 1 && bm == 1) return launch_gemm<BN, CG, 1, 1>(a, b, c, in, p, s);
+  if (am == 1 && bm == 0) return launch_gemm<BN, CG, 1, 0>(a, b, c, in, p, s);
   return set_error(-1, "bad operand major (%d,%d)", am, bm);
 }
 
@@ -391,10 +449,32 @@ int gemm_tf32(const float* A, long long lda, int a_major, const float* B, long l
   p.num_splits = splits;
   p.k_blocks = (K + kBK - 1) / kBK;
   p.C = C; p.ldc = ldc; p.c_split_stride = c_split_stride;
-  p.bias = bias; p.res = res; p.ldres = ldres; p.res_row_mod = res_row_mod;
-  p.aux = aux; p.ldaux = ldaux; p.act = act; p.round_out = round_out;
+  B200_CHECK_ARG(!(aux && res && res_row_mod == 0), "gemm: residual and tanh' inputs cannot be combined");
+  p.bias = bias; p.act = act; p.round_out = round_out;
+  p.res = (res && res_row_mod > 0) ? res : nullptr; p.ldres = ldres; p.res_row_mod = res_row_mod;
+  p.in_mode = aux ? 2 : ((res && res_row_mod == 0) ? 1 : 0);
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmIn;
+  {
+    const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)M, (unsigned long long)splits};
+    const unsigned long long strides[2] = {(unsigned long long)ldc * 4,
+                                           (unsigned long long)(splits > 1 ? c_split_stride : (long long)M * ldc) * 4};
+    const unsigned box[3] = {32, 32, 1};
+    B200_CHECK_ARG(splits == 1 || c_split_stride % 4 == 0, "gemm: c_split_stride %% 4");
+    int rc0 = make_tensor_map_f32(&tmC, C, 3, dims, strides, box, 0);
+    if (rc0) return rc0;
+    tmIn = tmC;
+    if (p.in_mode) {
+      const float* src = aux ? aux : res;
+      const long long ldin = aux ? ldaux : ldres;
+      B200_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0, "gemm: epilogue input must be 16-byte aligned");
+      const unsigned long long d2[2] = {(unsigned long long)N, (unsigned long long)M};
+      const unsigned long long s2[1] = {(unsigned long long)ldin * 4};
+      const unsigned b2[2] = {32, 32};
+      rc0 = make_tensor_map_f32(&tmIn, src, 2, d2, s2, b2, 0);
+      if (rc0) return rc0;
+    }
+  }
   const int ktot = K * splits;
   int rc;
   if (a_major == 0) rc = make_operand_tmap(&tmA, A, lda, M, ktot, 0, kBM);
@@ -407,8 +487,8 @@ int gemm_tf32(const float* A, long long lda, int a_major, const float* B, long l
 
 #define B200_GEMM_CASE(BN_)                                                                         \
   case BN_:                                                                                         \
-    return cta_group == 2 ? dispatch_major<BN_, 2>(a_major, b_major, tmA, tmB, p, stream)           \
-                          : dispatch_major<BN_, 1>(a_major, b_major, tmA, tmB, p, stream);
+    return cta_group == 2 ? dispatch_major<BN_, 2>(a_major, b_major, tmA, tmB, tmC, tmIn, p, stream) \
+                          : dispatch_major<BN_, 1>(a_major, b_major, tmA, tmB, tmC, tmIn, p, stream);
   switch (bn) {
     B200_GEMM_CASE(64)
     B200_GEMM_CASE(128)

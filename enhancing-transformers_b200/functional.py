@@ -20,7 +20,7 @@ Tensor = torch.Tensor
 
 # cta_group used for the big GEMMs (2 = CTA pair per 256-row tile); a module-level switch so
 # that tests and bench.py can pin it
-GEMM_CTA_GROUP = 1
+GEMM_CTA_GROUP = 2
 
 _shadow: Dict[Tuple[int, int], Tuple[int, Tensor]] = {}
 

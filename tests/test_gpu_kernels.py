@@ -201,10 +201,11 @@ def test_vq_full_size_properties():
 
 def test_vq_edge_cases():
     E = torch.randn(64, 32, device="cuda")
-    z = torch.zeros(4, 32, device="cuda")                 # zero rows: F.normalize gives 0, argmin well defined
-    out, loss, idx = ops.vq_fwd(z, E, 1, 0.25)
-    ref = O.vq_forward(z.cpu(), E.cpu())
-    assert torch.equal(idx.cpu()[:, 0], ref[2]) and torch.isfinite(loss)
+    z = torch.zeros(4, 32, device="cuda")                 # zero rows: F.normalize gives 0; every distance is |e_n|^2 ~ 1
+    out, loss, idx = ops.vq_fwd(z, E, 1, 0.25)            # (a 8192-way fp32 near-tie: any code within 1 ulp is correct)
+    en = torch.nn.functional.normalize(E, dim=-1)
+    d = (en ** 2).sum(-1)
+    assert torch.isfinite(loss) and (idx[:, 0] == idx[0, 0]).all() and d[idx[0, 0]] <= d.min() + 2.4e-7
     E2 = E.clone(); E2[5] = E2[3]                         # duplicate code: lowest index wins (torch.argmin)
     z = (E2[5] * 3.0).repeat(4, 1).contiguous()
     _, _, idx = ops.vq_fwd(z, E2, 1, 0.25)
