@@ -414,6 +414,13 @@ static int attn_fwd_launch(const float* qkv, float* out, float* lse, int B, int 
 }
 
 int attention_forward_tc(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int attention_backward_tc(const float*, const float*, const float*, const float*, float*, int, int, int, int, float, int,
+                          cudaStream_t);
+static bool use_mma_bwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200VQ_ATTN_BWD"); v = (e && e[0] == 'm') ? 1 : 0; }
+  return v == 1;
+}
 
 // B200VQ_ATTN_FWD=mma selects the v1 mma.sync kernel (kept for A/B measurements); default is tcgen05
 static bool use_mma_fwd() {
@@ -460,6 +467,7 @@ int attention_backward(const float* qkv, const float* out, const float* lse, con
   const long long warps = (long long)B * N * heads;
   attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(out, dout, delta, B, N, heads, dh);
   B200_LAUNCH_OK("attn_delta_kernel");
+  if (!use_mma_bwd()) return attention_backward_tc(qkv, dout, lse, delta, dqkv, B, N, heads, dh, scale, round_out, stream);
   if (dh == 64) return attn_bwd_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
   return attn_bwd_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
 }

@@ -282,6 +282,504 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   return 0;
 }
 
+// =============================================================================================
+// backward on tcgen05 (two kernels, no atomics; scores recomputed from the saved log-sum-exp)
+//
+//   dKV kernel: work item = (batch, head, 128-key tile); loops over 64-query sub-tiles:
+//       S^T = K Q^T, dP^T = V dO^T            (SS MMAs, 128 x 64 accumulators, two buffers each)
+//       P^T = exp2(S^T c - lse[q]),  dS^T = P^T (dP^T - delta[q])     (softmax warps, thread = key row,
+//                                                    written back over S^T / dP^T as tf32)
+//       dV += P^T dO,  dK += dS^T Q           (TS MMAs: A from TMEM, B = dO / Q as MN-major tiles)
+//   dQ kernel: work item = (batch, head, 128-query tile); loops over 64-key sub-tiles:
+//       S = Q K^T, dP = dO V^T ; dS = exp2(S c - lse) (dP - delta) ; dQ += dS K
+// Q / dO (resp. K) are needed both as K-major operands (SWIZZLE_128B) and as MN-major operands
+// (SWIZZLE_128B_BASE32B): TMA fetches the same global tile twice with two tensor maps.
+// =============================================================================================
+struct AttnBwdParams {
+  const float* lse;     // [B*heads*N]
+  const float* delta;   // [B*heads*N]
+  float* dqkv;          // [B*N, 3*heads*DH]
+  int B, N, heads;
+  int tiles128, sub64, total_items;
+  float scale;
+  int round_out;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ64,
+                       const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmQM,
+                       const __grid_constant__ CUtensorMap tmDOM, const AttnBwdParams p) {
+  constexpr int KB = DH / 32;
+  constexpr int T128 = 128 * DH * 4;   // K or V tile
+  constexpr int T64 = 64 * DH * 4;     // one 64-row operand copy
+  constexpr int KBLK128 = 128 * 128, KBLK64 = 64 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Ks = smem;
+  uint8_t* Vs = smem + T128;
+  uint8_t* St = smem + 2 * T128;        // stage s at St + s*4*T64: [QK | DK | QM | DM]
+  float* Ls = reinterpret_cast<float*>(smem + 2 * T128 + 8 * T64);   // [2][64] lse * log2e
+  float* Es = Ls + 128;                                              // [2][64] delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Es + 128);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* qk_full = bars + 2;    // [2]
+  uint64_t* qk_empty = bars + 4;   // [2]
+  uint64_t* qm_full = bars + 6;    // [2]
+  uint64_t* qm_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* acc_full = bars + 14;
+  uint64_t* acc_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmDO64);
+    tma_prefetch_desc(&tmQM); tma_prefetch_desc(&tmDOM);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1);
+      mbar_init(&qm_full[s], 1); mbar_init(&qm_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int NS = p.sub64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sub_it = 0, item_it = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+        const int kt = w % p.tiles128;
+        const int bh = w / p.tiles128;
+        const int h = bh % p.heads, b = bh / p.heads;
+        mbar_wait(kv_empty, (item_it & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full, 2 * T128);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(Ks + kb * KBLK128, &tmKV, kv_full, inner + h * DH + kb * 32, kt * 128, b);
+          tma_load_3d(Vs + kb * KBLK128, &tmKV, kv_full, 2 * inner + h * DH + kb * 32, kt * 128, b);
+        }
+        for (int i = 0; i < NS; ++i, ++sub_it) {
+          const int s = sub_it & 1;
+          const uint32_t ph = (sub_it >> 1) & 1;
+          uint8_t* st = St + s * 4 * T64;
+          mbar_wait(&qk_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&qk_full[s], 2 * T64);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_3d(st + kb * KBLK64, &tmQ64, &qk_full[s], h * DH + kb * 32, i * 64, b);
+            tma_load_3d(st + T64 + kb * KBLK64, &tmDO64, &qk_full[s], h * DH + kb * 32, i * 64, b);
+          }
+          mbar_wait(&qm_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&qm_full[s], 2 * T64);
+          tma_load_4d(st + 2 * T64, &tmQM, &qm_full[s], 0, i * 64, (h * DH) / 32, b);
+          tma_load_4d(st + 3 * T64, &tmDOM, &qm_full[s], 0, i * 64, (h * DH) / 32, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+      uint32_t sd_it = 0, dv_it = 0, item_it = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+        mbar_wait(kv_full, item_it & 1);
+        tcgen05_fence_after();
+        const uint32_t ka = smem_u32(Ks), va = smem_u32(Vs);
+        for (int i = 0; i <= NS; ++i) {
+          if (i < NS) {
+            const int s = sd_it & 1;
+            mbar_wait(&qk_full[s], (sd_it >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t qa = smem_u32(St + s * 4 * T64), da = qa + T64;
+#pragma unroll
+            for (int k = 0; k < DH / 8; ++k) {
+              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+              umma_tf32<1>(tmem_base + s * 64, make_smem_desc(ka + offa, 16, 1024, kLayoutSw128),
+                           make_smem_desc(qa + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+            }
+#pragma unroll
+            for (int k = 0; k < DH / 8; ++k) {
+              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+              umma_tf32<1>(tmem_base + 128 + s * 64, make_smem_desc(va + offa, 16, 1024, kLayoutSw128),
+                           make_smem_desc(da + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+            }
+            umma_commit<1>(&s_full[s]);
+            umma_commit<1>(&qk_empty[s]);
+            if (i == NS - 1) umma_commit<1>(kv_empty);
+            ++sd_it;
+          }
+          if (i >= 1) {
+            const int s = dv_it & 1;
+            mbar_wait(&p_full[s], (dv_it >> 1) & 1);
+            mbar_wait(&qm_full[s], (dv_it >> 1) & 1);
+            if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t qm = smem_u32(St + s * 4 * T64 + 2 * T64), dm = qm + T64;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // dV += P^T dO
+              umma_tf32_ts(tmem_base + 256, tmem_base + s * 64 + k * 8,
+                           make_smem_desc(dm + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // dK += dS^T Q
+              umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8,
+                           make_smem_desc(qm + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+            umma_commit<1>(&qm_empty[s]);
+            if (i == NS) umma_commit<1>(acc_full);
+            ++dv_it;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;          // 0..127 among the softmax threads
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int kt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
+      const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it & 1;
+        if (et < 64) {
+          const int qi = i * 64 + et;
+          Ls[s * 64 + et] = qi < p.N ? lb[qi] * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
+          Es[s * 64 + et] = qi < p.N ? eb[qi] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32], g[32];
+          tmem_ld_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
+          tmem_ld_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Ls[s * 64 + cc * 32 + j]));
+            const float ds = pr * (__uint_as_float(g[j]) - Es[s * 64 + cc * 32 + j]);
+            v[j] = __float_as_uint(round_tf32(pr));
+            g[j] = __float_as_uint(round_tf32(ds));
+          }
+          tmem_st_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
+          tmem_st_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      // item epilogue: dV, dK rows of this thread's key
+      mbar_wait(acc_full, item_it & 1);
+      tcgen05_fence_after();
+      const int key = kt * 128 + q * 32 + lane;
+      const long long ld = 3ll * inner;
+      float* dkp = p.dqkv + ((long long)b * p.N + key) * ld + inner + h * DH;
+      float* dvp = dkp + inner;
+#pragma unroll 1
+      for (int cc = 0; cc < DH / 32; ++cc) {
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + 256 + cc * 32, v);   // dV
+        tmem_ld_32x32(tmem_base + lane_off + 320 + cc * 32, g);   // dK
+        tmem_ld_wait();
+        if (key < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            float4 k4 = make_float4(__uint_as_float(g[j]) * p.scale, __uint_as_float(g[j + 1]) * p.scale,
+                                    __uint_as_float(g[j + 2]) * p.scale, __uint_as_float(g[j + 3]) * p.scale);
+            if (p.round_out) {
+              a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w);
+              k4.x = round_tf32(k4.x); k4.y = round_tf32(k4.y); k4.z = round_tf32(k4.z); k4.w = round_tf32(k4.w);
+            }
+            *reinterpret_cast<float4*>(dvp + cc * 32 + j) = a;
+            *reinterpret_cast<float4*>(dkp + cc * 32 + j) = k4;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
+                      const __grid_constant__ CUtensorMap tmKV64, const __grid_constant__ CUtensorMap tmKM,
+                      const AttnBwdParams p) {
+  constexpr int KB = DH / 32;
+  constexpr int T128 = 128 * DH * 4;
+  constexpr int T64 = 64 * DH * 4;
+  constexpr int KBLK128 = 128 * 128, KBLK64 = 64 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ds = smem + T128;
+  uint8_t* St = smem + 2 * T128;        // stage s at St + s*3*T64: [KK | VK | KM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 6 * T64);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kk_full = bars + 2;    // [2]
+  uint64_t* kk_empty = bars + 4;   // [2]
+  uint64_t* km_full = bars + 6;    // [2]
+  uint64_t* km_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* acc_full = bars + 14;
+  uint64_t* acc_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmKV64); tma_prefetch_desc(&tmKM);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kk_full[s], 1); mbar_init(&kk_empty[s], 1);
+      mbar_init(&km_full[s], 1); mbar_init(&km_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int NS = p.sub64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sub_it = 0, item_it = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+        const int qt = w % p.tiles128;
+        const int bh = w / p.tiles128;
+        const int h = bh % p.heads, b = bh / p.heads;
+        mbar_wait(q_empty, (item_it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 2 * T128);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(Qs + kb * KBLK128, &tmQ128, q_full, h * DH + kb * 32, qt * 128, b);
+          tma_load_3d(Ds + kb * KBLK128, &tmDO128, q_full, h * DH + kb * 32, qt * 128, b);
+        }
+        for (int i = 0; i < NS; ++i, ++sub_it) {
+          const int s = sub_it & 1;
+          const uint32_t ph = (sub_it >> 1) & 1;
+          uint8_t* st = St + s * 3 * T64;
+          mbar_wait(&kk_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kk_full[s], 2 * T64);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_3d(st + kb * KBLK64, &tmKV64, &kk_full[s], inner + h * DH + kb * 32, i * 64, b);
+            tma_load_3d(st + T64 + kb * KBLK64, &tmKV64, &kk_full[s], 2 * inner + h * DH + kb * 32, i * 64, b);
+          }
+          mbar_wait(&km_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&km_full[s], T64);
+          tma_load_4d(st + 2 * T64, &tmKM, &km_full[s], 0, i * 64, (inner + h * DH) / 32, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+      uint32_t sd_it = 0, dq_it = 0, item_it = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+        mbar_wait(q_full, item_it & 1);
+        tcgen05_fence_after();
+        const uint32_t qa = smem_u32(Qs), da = smem_u32(Ds);
+        for (int i = 0; i <= NS; ++i) {
+          if (i < NS) {
+            const int s = sd_it & 1;
+            mbar_wait(&kk_full[s], (sd_it >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t kk = smem_u32(St + s * 3 * T64), vk = kk + T64;
+#pragma unroll
+            for (int k = 0; k < DH / 8; ++k) {
+              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+              umma_tf32<1>(tmem_base + s * 64, make_smem_desc(qa + offa, 16, 1024, kLayoutSw128),
+                           make_smem_desc(kk + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+            }
+#pragma unroll
+            for (int k = 0; k < DH / 8; ++k) {
+              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+              umma_tf32<1>(tmem_base + 128 + s * 64, make_smem_desc(da + offa, 16, 1024, kLayoutSw128),
+                           make_smem_desc(vk + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+            }
+            umma_commit<1>(&s_full[s]);
+            umma_commit<1>(&kk_empty[s]);
+            if (i == NS - 1) umma_commit<1>(q_empty);
+            ++sd_it;
+          }
+          if (i >= 1) {
+            const int s = dq_it & 1;
+            mbar_wait(&p_full[s], (dq_it >> 1) & 1);
+            mbar_wait(&km_full[s], (dq_it >> 1) & 1);
+            if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t km = smem_u32(St + s * 3 * T64 + 2 * T64);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // dQ += dS K
+              umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8,
+                           make_smem_desc(km + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+            umma_commit<1>(&km_empty[s]);
+            if (i == NS) umma_commit<1>(acc_full);
+            ++dq_it;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int row = qt * 128 + q * 32 + lane;
+      const long long sidx = ((long long)b * p.heads + h) * p.N + row;
+      const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
+      const float dl = row < p.N ? p.delta[sidx] : 0.f;
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it & 1;
+        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+        const int kv_left = p.N - i * 64;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32], g[32];
+          tmem_ld_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
+          tmem_ld_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = (cc * 32 + j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
+            g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
+          }
+          tmem_st_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      mbar_wait(acc_full, item_it & 1);
+      tcgen05_fence_after();
+      float* dqp = p.dqkv + ((long long)b * p.N + row) * (3ll * inner) + h * DH;
+#pragma unroll 1
+      for (int cc = 0; cc < DH / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_off + 256 + cc * 32, v);
+        tmem_ld_wait();
+        if (row < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 a = make_float4(__uint_as_float(v[j]) * p.scale, __uint_as_float(v[j + 1]) * p.scale,
+                                   __uint_as_float(v[j + 2]) * p.scale, __uint_as_float(v[j + 3]) * p.scale);
+            if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
+            *reinterpret_cast<float4*>(dqp + cc * 32 + j) = a;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// K-major (SWIZZLE_128B) view of a [B*N, ld] matrix as {ld, N, B}, box {32, rows, 1}
+static int make_kmajor_map(CUtensorMap* out, const float* ptr, long long ld, int N, int B, int box_rows) {
+  const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
+  const unsigned long long strides[2] = {(unsigned long long)ld * 4, (unsigned long long)N * ld * 4};
+  const unsigned box[3] = {32, (unsigned)box_rows, 1};
+  return make_tensor_map_f32(out, ptr, 3, dims, strides, box, 0);
+}
+// MN-major (SWIZZLE_128B_BASE32B) view as {32, N, ld/32, B}, box {32, rows, atoms, 1}
+static int make_mnmajor_map(CUtensorMap* out, const float* ptr, long long ld, int N, int B, int box_rows, int atoms) {
+  const unsigned long long dims[4] = {32, (unsigned long long)N, (unsigned long long)(ld / 32), (unsigned long long)B};
+  const unsigned long long strides[3] = {(unsigned long long)ld * 4, 128, (unsigned long long)N * ld * 4};
+  const unsigned box[4] = {32, (unsigned)box_rows, (unsigned)atoms, 1};
+  return make_tensor_map_f32(out, ptr, 4, dims, strides, box, 1);
+}
+
+template <int DH>
+static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B,
+                              int N, int heads, float scale, int round_out, cudaStream_t stream) {
+  const int inner = heads * DH;
+  const long long ld = 3ll * inner;
+  CUtensorMap tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmDO128;
+  int rc;
+  if ((rc = make_kmajor_map(&tmKV128, qkv, ld, N, B, 128))) return rc;
+  if ((rc = make_kmajor_map(&tmQ64, qkv, ld, N, B, 64))) return rc;
+  if ((rc = make_kmajor_map(&tmDO64, dout, inner, N, B, 64))) return rc;
+  if ((rc = make_kmajor_map(&tmDO128, dout, inner, N, B, 128))) return rc;
+  if ((rc = make_mnmajor_map(&tmQM, qkv, ld, N, B, 64, DH / 32))) return rc;
+  if ((rc = make_mnmajor_map(&tmDOM, dout, inner, N, B, 64, DH / 32))) return rc;
+  AttnBwdParams p;
+  p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.B = B; p.N = N; p.heads = heads;
+  p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
+  p.total_items = p.tiles128 * heads * B;
+  p.scale = scale; p.round_out = round_out;
+  constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + 1024 + 256 + 1024;
+  constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + 256 + 1024;
+  auto k1 = attn_bwd_dkv_tc_kernel<DH>;
+  auto k2 = attn_bwd_dq_tc_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
+    B200_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+    configured = true;
+  }
+  int grid = num_sms();
+  if (grid > p.total_items) grid = p.total_items;
+  k1<<<grid, kAtcThreads, smem_kv, stream>>>(tmKV128, tmQ64, tmDO64, tmQM, tmDOM, p);
+  B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
+  k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, p);
+  B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
+  return 0;
+}
+
+int attention_backward_tc(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B, int N,
+                          int heads, int dh, float scale, int round_out, cudaStream_t stream) {
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
+                 "attention: qkv/dout must be 16-byte aligned");
+  if (dh == 64) return attn_bwd_tc_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
+  return attn_bwd_tc_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
+}
+
 int attention_forward_tc(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale, int round_out,
                          cudaStream_t stream) {
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
