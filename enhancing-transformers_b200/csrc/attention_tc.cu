@@ -16,7 +16,14 @@
 
 namespace b200 {
 
-constexpr int kAtcThreads = 192;
+constexpr int kAtcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
+constexpr int kAtcSoftmaxThreads = 256;
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]) {
+  if constexpr (NC == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 constexpr float kLog2eF = 1.4426950408889634f;
 
 struct AttnTcParams {
@@ -51,6 +58,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   uint64_t* o_full = bars + 14;   // [2]
   uint64_t* o_empty = bars + 16;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* xch = reinterpret_cast<float*>(bars + 20);   // [3][2][128] row-max (double buffered) and row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -61,8 +69,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -149,7 +157,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
+    // A query row is shared by two threads (warps w and w+4 address the same TMEM lanes): each
+    // takes 64 of the 128 scores of a tile and half of the head dim of the output; the row max
+    // (per tile) and the row sum (once per item) are exchanged through shared memory.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const float c = p.scale * kLog2eF;
@@ -158,22 +171,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
-      float o[DH];
+      float o[OC];
 #pragma unroll
-      for (int i = 0; i < DH; ++i) o[i] = 0.f;
+      for (int i = 0; i < OC; ++i) o[i] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
       auto accumulate_pv = [&](uint32_t it, float alpha) {
         const int sp = it & 1;
         mbar_wait(&o_full[sp], (it >> 1) & 1);
         tcgen05_fence_after();
+        uint32_t v[OC];
+        tmem_ld_cols<OC>(tmem_base + lane_off + 256 + sp * 64 + half * OC, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int cc = 0; cc < DH / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_off + 256 + sp * 64 + cc * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[cc * 32 + i] = fmaf(o[cc * 32 + i], alpha, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[sp]);
@@ -182,11 +192,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         const int s = t_it & 1;
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t sa = tmem_base + lane_off + s * 128;
-        const int kv_left = p.N - j * 128;       // keys >= kv_left in this tile are padding
+        const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
+        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[32];
           tmem_ld_32x32(sa + cc * 32, v);
           tmem_ld_wait();
@@ -196,12 +206,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             mx = fmaxf(mx, x);
           }
         }
+        float* xs = xch + (t_it & 1) * 256;
+        xs[half * 128 + row_in_tile] = mx;
+        softmax_bar();
+        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
         float sum = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[32];
           tmem_ld_32x32(sa + cc * 32, v);
           tmem_ld_wait();
@@ -224,18 +238,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         m = m_new;
       }
       accumulate_pv(t_it - 1, alpha_prev);
+      float* ls = xch + 512;
+      ls[half * 128 + row_in_tile] = l;
+      softmax_bar();
+      l += ls[(half ^ 1) * 128 + row_in_tile];
       const int row = qt * 128 + row_in_tile;
       if (row < p.N) {
         const float inv = 1.f / l;
-        float* op = p.out + ((long long)b * p.N + row) * inner + h * DH;
+        float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
 #pragma unroll
-        for (int i = 0; i < DH; i += 4) {
+        for (int i = 0; i < OC; i += 4) {
           float4 r = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
           if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
           *reinterpret_cast<float4*>(op + i) = r;
         }
-        p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
+        if (half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
       }
+      softmax_bar();   // ls is rewritten by the next item only after everyone has read it
     }
   }
   tcgen05_fence_before();
@@ -271,7 +290,7 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 256;
+  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 256 + 3 * 256 * 4;
   auto kern = attn_fwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
@@ -342,9 +361,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1);
       mbar_init(&qm_full[s], 1); mbar_init(&qm_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
     }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -442,8 +461,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       }
     }
   } else {
+    // 8 softmax warps: warps w and w+4 share a TMEM lane quarter (key rows) and split the 64
+    // query columns of a sub-tile; at the end of an item one half stores dV, the other dK.
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;          // 0..127 among the softmax threads
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;          // 0..255 among the softmax threads
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
@@ -460,55 +482,53 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           Ls[s * 64 + et] = qi < p.N ? lb[qi] * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
           Es[s * 64 + et] = qi < p.N ? eb[qi] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        softmax_bar();
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32], g[32];
-          tmem_ld_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
-          tmem_ld_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
-          tmem_ld_wait();
+        const int col = s * 64 + half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Ls[s * 64 + cc * 32 + j]));
-            const float ds = pr * (__uint_as_float(g[j]) - Es[s * 64 + cc * 32 + j]);
-            v[j] = __float_as_uint(round_tf32(pr));
-            g[j] = __float_as_uint(round_tf32(ds));
+        for (int j = 0; j < 32; j += 4) {
+          const float4 L = *reinterpret_cast<const float4*>(&Ls[col + j]);
+          const float4 E = *reinterpret_cast<const float4*>(&Es[col + j]);
+          const float Lv[4] = {L.x, L.y, L.z, L.w}, Ev[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float pr = ex2_approx(fmaf(__uint_as_float(v[j + u]), c, -Lv[u]));
+            const float ds = pr * (__uint_as_float(g[j + u]) - Ev[u]);
+            v[j + u] = __float_as_uint(round_tf32(pr));
+            g[j + u] = __float_as_uint(round_tf32(ds));
           }
-          tmem_st_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
-          tmem_st_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
         }
+        tmem_st_32x32(tmem_base + lane_off + col, v);
+        tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
       }
-      // item epilogue: dV, dK rows of this thread's key
+      // item epilogue: this thread's key row of dV (half 0) or dK (half 1)
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
       const int key = kt * 128 + q * 32 + lane;
       const long long ld = 3ll * inner;
-      float* dkp = p.dqkv + ((long long)b * p.N + key) * ld + inner + h * DH;
-      float* dvp = dkp + inner;
+      float* dst = p.dqkv + ((long long)b * p.N + key) * ld + (half == 0 ? 2 * inner : inner) + h * DH;
+      const float mul = half == 0 ? 1.f : p.scale;
 #pragma unroll 1
       for (int cc = 0; cc < DH / 32; ++cc) {
-        uint32_t v[32], g[32];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + cc * 32, v);   // dV
-        tmem_ld_32x32(tmem_base + lane_off + 320 + cc * 32, g);   // dK
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_off + (half == 0 ? 256 : 320) + cc * 32, v);
         tmem_ld_wait();
         if (key < p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            float4 k4 = make_float4(__uint_as_float(g[j]) * p.scale, __uint_as_float(g[j + 1]) * p.scale,
-                                    __uint_as_float(g[j + 2]) * p.scale, __uint_as_float(g[j + 3]) * p.scale);
-            if (p.round_out) {
-              a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w);
-              k4.x = round_tf32(k4.x); k4.y = round_tf32(k4.y); k4.z = round_tf32(k4.z); k4.w = round_tf32(k4.w);
-            }
-            *reinterpret_cast<float4*>(dvp + cc * 32 + j) = a;
-            *reinterpret_cast<float4*>(dkp + cc * 32 + j) = k4;
+            float4 a = make_float4(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul, __uint_as_float(v[j + 2]) * mul,
+                                   __uint_as_float(v[j + 3]) * mul);
+            if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
+            *reinterpret_cast<float4*>(dst + cc * 32 + j) = a;
           }
         }
       }
@@ -559,9 +579,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kk_full[s], 1); mbar_init(&kk_empty[s], 1);
       mbar_init(&km_full[s], 1); mbar_init(&km_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
     }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -655,6 +675,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
@@ -670,20 +692,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         const int s = t_it & 1;
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-        const int kv_left = p.N - i * 64;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32], g[32];
-          tmem_ld_32x32(tmem_base + lane_off + s * 64 + cc * 32, v);
-          tmem_ld_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
-          tmem_ld_wait();
+        const int col = s * 64 + half * 32;
+        const int kv_left = p.N - i * 64 - half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pr = (cc * 32 + j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
-            g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
-          }
-          tmem_st_32x32(tmem_base + lane_off + 128 + s * 64 + cc * 32, g);
+        for (int j = 0; j < 32; ++j) {
+          const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
+          g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
         }
+        tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -691,19 +711,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
-      float* dqp = p.dqkv + ((long long)b * p.N + row) * (3ll * inner) + h * DH;
-#pragma unroll 1
-      for (int cc = 0; cc < DH / 32; ++cc) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + cc * 32, v);
+      float* dqp = p.dqkv + ((long long)b * p.N + row) * (3ll * inner) + h * DH + half * OC;
+      {
+        uint32_t v[OC];
+        tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, v);
         tmem_ld_wait();
         if (row < p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < OC; j += 4) {
             float4 a = make_float4(__uint_as_float(v[j]) * p.scale, __uint_as_float(v[j + 1]) * p.scale,
                                    __uint_as_float(v[j + 2]) * p.scale, __uint_as_float(v[j + 3]) * p.scale);
             if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
-            *reinterpret_cast<float4*>(dqp + cc * 32 + j) = a;
+            *reinterpret_cast<float4*>(dqp + j) = a;
           }
         }
       }

@@ -156,29 +156,43 @@ __global__ void ln_param_reduce_kernel(const float* __restrict__ part, int npart
   if (j < D) dgamma[j] = a; else dbeta[j - D] = a;
 }
 
-// column sums of X[M, N] (bias gradients): stage 1 writes part[blk][N]
+// column sums of X[M, N] (bias gradients): stage 1 writes part[blockIdx.y][N].
+// grid = (ceil(N/128), R): a CTA owns 128 columns (32 float4 lanes) and every R-th group of 8 rows,
+// accumulates in registers over its rows (4 independent 16-byte loads in flight per thread) and
+// reduces across its 8 row-lanes once at the end.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ part) {
-  // block = 32 x 8 threads: threadIdx.x spans 32 float4 columns, threadIdx.y strides rows
   __shared__ float4 sm[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;          // float4 column
   const int nv = N >> 2;
-  for (int cb = 0; cb < nv; cb += 32) {
-    const int c = cb + tx;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < nv)
-      for (int r = blockIdx.x * 8 + ty; r < M; r += gridDim.x * 8) {
-        const float4 v = *reinterpret_cast<const float4*>(X + (size_t)r * ld + c * 4);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-    sm[ty][tx] = a;
-    __syncthreads();
-    if (ty == 0 && c < nv) {
-      float4 s = sm[0][tx];
-      for (int w = 1; w < 8; ++w) { s.x += sm[w][tx].x; s.y += sm[w][tx].y; s.z += sm[w][tx].z; s.w += sm[w][tx].w; }
-      *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * N + c * 4) = s;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  if (c < nv) {
+    const long long stride = 8ll * gridDim.y;
+    long long r = (long long)blockIdx.y * 8 + ty;
+    const float* base = X + c * 4;
+    for (; r + 3 * stride < M; r += 4 * stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + r * ld);
+      const float4 v1 = *reinterpret_cast<const float4*>(base + (r + stride) * ld);
+      const float4 v2 = *reinterpret_cast<const float4*>(base + (r + 2 * stride) * ld);
+      const float4 v3 = *reinterpret_cast<const float4*>(base + (r + 3 * stride) * ld);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
     }
-    __syncthreads();
+    for (; r < M; r += stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + r * ld);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+  }
+  a0.x += a1.x + a2.x + a3.x; a0.y += a1.y + a2.y + a3.y; a0.z += a1.z + a2.z + a3.z; a0.w += a1.w + a2.w + a3.w;
+  sm[ty][tx] = a0;
+  __syncthreads();
+  if (ty == 0 && c < nv) {
+    float4 t = sm[0][tx];
+    for (int w = 1; w < 8; ++w) { t.x += sm[w][tx].x; t.y += sm[w][tx].y; t.z += sm[w][tx].z; t.w += sm[w][tx].w; }
+    *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * N + c * 4) = t;
   }
 }
 
@@ -330,18 +344,21 @@ int layernorm_backward(const float* dy, const float* x, const float* mean, const
   return 0;
 }
 
-int colsum_blocks() { return num_sms() * 2; }
-size_t colsum_workspace_bytes(int N) { return (size_t)colsum_blocks() * N * sizeof(float); }
+constexpr int kColsumMaxSplits = 64;
+size_t colsum_workspace_bytes(int N) { return (size_t)kColsumMaxSplits * N * sizeof(float); }
 
 int colsum(const float* X, long long ld, int M, int N, float* out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   B200_CHECK_ARG(M > 0 && N > 0 && N % 4 == 0 && ld % 4 == 0, "colsum: N and ld must be multiples of 4");
   B200_CHECK_ARG(ws_bytes >= colsum_workspace_bytes(N), "colsum: workspace too small");
-  int blocks = colsum_blocks();
-  if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
+  const int colblocks = (N / 4 + 31) / 32;
+  int splits = (num_sms() * 8 + colblocks - 1) / colblocks;
+  if (splits > kColsumMaxSplits) splits = kColsumMaxSplits;
+  if (splits > (M + 7) / 8) splits = (M + 7) / 8;
+  if (splits < 1) splits = 1;
   float* part = static_cast<float*>(workspace);
-  colsum_kernel<<<blocks, 256, 0, stream>>>(X, ld, M, N, part);
+  colsum_kernel<<<dim3(colblocks, splits), 256, 0, stream>>>(X, ld, M, N, part);
   B200_LAUNCH_OK("colsum_kernel");
-  colpart_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(part, blocks, N, out);
+  colpart_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(part, splits, N, out);
   B200_LAUNCH_OK("colpart_reduce_kernel");
   return 0;
 }

@@ -362,6 +362,36 @@ def g_model_perf():
                 break
 
 
+def g_precision():
+    """error of the tf32 path vs the oracle evaluated in fp64 on the GPU, per stage"""
+    import torch
+    from oracle import vitvq_oracle as O
+    import enhancing_transformers_b200 as etb
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, B in (("small", 4), ("base", 4)):
+        cfg = O.CONFIGS[name]
+        sd = O.init_vitvq_sd(cfg, seed=0)
+        img = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+        sd64 = {k: v.double().cuda() for k, v in sd.items()}
+        p, g = cfg["patch_size"], cfg["image_size"] // cfg["patch_size"]
+        e, d = cfg["encoder"], cfg["decoder"]
+        with torch.no_grad():
+            h64 = O.vit_encoder(sd64, img.double().cuda(), patch=p, depth=e["depth"], heads=e["heads"], prefix="encoder.")
+            z64 = h64 @ sd64["pre_quant.weight"].t() + sd64["pre_quant.bias"]
+            mods = _load_modules(cfg, sd)
+            enc, dec, vq, pre, post = mods
+            h = enc(img.cuda()); z = pre(h)
+            zq, _, idx = vq(z)
+            zq64, _, idx64 = O.vq_forward(z64.float(), sd["quantizer.embedding.weight"].cuda())
+            rec = dec(post(zq))
+            t64 = zq.double() @ sd64["post_quant.weight"].t() + sd64["post_quant.bias"]
+            rec64 = O.vit_decoder(sd64, t64, patch=p, depth=d["depth"], heads=d["heads"], grid_hw=(g, g), prefix="decoder.")
+        print(f"{name}: enc relmax {relerr(h.double(), h64):.2e} rel-l2 {((h.double()-h64).norm()/h64.norm()).item():.2e} | z relmax {relerr(z.double(), z64):.2e} | "
+              f"idx agree {(idx == idx64).float().mean().item():.5f} | dec-only (same codes) relmax {relerr(rec.double(), rec64):.2e} rel-l2 {((rec.double()-rec64).norm()/rec64.norm()).item():.2e}", flush=True)
+        del mods
+        etb.functional.clear_shadow_cache(); torch.cuda.empty_cache()
+
+
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
 
 if __name__ == "__main__":
