@@ -475,12 +475,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
+      // lse / delta of a sub-tile are fetched one sub-tile ahead into registers so that the global
+      // load latency never sits between the barrier below and the score tile
+      float nl = INFINITY, ne = 0.f;                                  // +inf -> P = 0 for padded queries
+      if (et < 64 && et < p.N) { nl = lb[et] * kLog2eF; ne = eb[et]; }
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
         if (et < 64) {
-          const int qi = i * 64 + et;
-          Ls[s * 64 + et] = qi < p.N ? lb[qi] * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
-          Es[s * 64 + et] = qi < p.N ? eb[qi] : 0.f;
+          Ls[s * 64 + et] = nl;
+          Es[s * 64 + et] = ne;
+          const int qi = (i + 1) * 64 + et;
+          nl = INFINITY; ne = 0.f;
+          if (i + 1 < NS && qi < p.N) { nl = lb[qi] * kLog2eF; ne = eb[qi]; }
         }
         softmax_bar();
         mbar_wait(&s_full[s], (t_it >> 1) & 1);

@@ -57,11 +57,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// round-to-nearest fp32 -> tf32 (10-bit mantissa), result kept in an fp32 container
+// round-to-nearest (ties away from zero, like cvt.rna.tf32.f32) fp32 -> tf32 (10-bit mantissa),
+// result kept in an fp32 container with the low 13 bits cleared.  Done with two integer ops on
+// the ALU pipe: cvt.rna.tf32 issues on the XU pipe (16 lanes/clk/SM, shared with ex2) and was the
+// measured bottleneck of the attention softmax warps.
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
