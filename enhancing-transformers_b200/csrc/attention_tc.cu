@@ -117,19 +117,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
         mbar_wait(q_full, item_it & 1);
         tcgen05_fence_after();
-        const uint32_t qa = smem_u32(Qs);
+        const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
         for (int j = 0; j <= T; ++j) {
           if (j < T) {
             const int s = s_it & 1;
             const uint32_t ph = (s_it >> 1) & 1;
             mbar_wait(&k_full[s], ph);
             tcgen05_fence_after();
-            const uint32_t ka = smem_u32(Ks + s * TILE_BYTES);
+            const uint64_t kd = make_smem_desc(smem_u32(Ks + s * TILE_BYTES), 16, 1024, kLayoutSw128);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 128, make_smem_desc(qa + off, 16, 1024, kLayoutSw128),
-                           make_smem_desc(ka + off, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+              umma_tf32<1>(tmem_base + s * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
             }
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&k_empty[s]);
@@ -143,11 +142,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             mbar_wait(&v_full[s], ph);
             mbar_wait(&o_empty[s], ph ^ 1);
             tcgen05_fence_after();
-            const uint32_t va = smem_u32(Vs + s * TILE_BYTES);
+            const uint64_t vd = make_smem_desc(smem_u32(Vs + s * TILE_BYTES), KBLK_BYTES, 512, kLayoutSw128Base32);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              umma_tf32_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8,
-                           make_smem_desc(va + k * 1024, KBLK_BYTES, 512, kLayoutSw128Base32), idesc_o, k != 0);
+              umma_tf32_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, k != 0);
             umma_commit<1>(&o_full[s]);
             umma_commit<1>(&v_empty[s]);
             ++pv_it;
@@ -194,17 +192,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         tcgen05_fence_after();
         const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
         const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
+        // one pass over TMEM: the thread's 64 scores stay in registers between max and exp
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(sa, v0);
+        tmem_ld_32x32(sa + 32, v1);
+        tmem_ld_wait();
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(sa + cc * 32, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (cc * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY;
-            mx = fmaxf(mx, x);
-          }
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_left) v0[i] = 0xff800000u;          // -inf: padded key columns
+          if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
         }
         float* xs = xch + (t_it & 1) * 256;
         xs[half * 128 + row_in_tile] = mx;
@@ -213,21 +211,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
-        float sum = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(sa + cc * 32, v);
-          tmem_ld_wait();
+        float sum = 0.f, sum1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (cc * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY;
-            const float e = ex2_approx(fmaf(x, c, -mc));
-            sum += e;
-            v[i] = __float_as_uint(round_tf32(e));
-          }
-          tmem_st_32x32(sa + cc * 32, v);
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
+          sum += e0; sum1 += e1;
+          v0[i] = __float_as_uint(round_tf32(e0));
+          v1[i] = __float_as_uint(round_tf32(e1));
         }
+        sum += sum1;
+        tmem_st_32x32(sa, v0);
+        tmem_st_32x32(sa + 32, v1);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -314,6 +309,10 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
 // Q / dO (resp. K) are needed both as K-major operands (SWIZZLE_128B) and as MN-major operands
 // (SWIZZLE_128B_BASE32B): TMA fetches the same global tile twice with two tensor maps.
 // =============================================================================================
+// cycle counters of block 0 (development aid, read back with b200vq_debug_counters): filled only by the dQ kernel
+__device__ long long g_attn_dbg[32];
+#define DBG_T(var) const long long var = clock64()
+
 struct AttnBwdParams {
   const float* lse;     // [B*heads*N]
   const float* delta;   // [B*heads*N]
@@ -414,24 +413,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
         mbar_wait(kv_full, item_it & 1);
         tcgen05_fence_after();
-        const uint32_t ka = smem_u32(Ks), va = smem_u32(Vs);
+        const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
+        const uint64_t vd = make_smem_desc(smem_u32(Vs), 16, 1024, kLayoutSw128);
         for (int i = 0; i <= NS; ++i) {
           if (i < NS) {
             const int s = sd_it & 1;
             mbar_wait(&qk_full[s], (sd_it >> 1) & 1);
             tcgen05_fence_after();
-            const uint32_t qa = smem_u32(St + s * 4 * T64), da = qa + T64;
+            const uint64_t qd = make_smem_desc(smem_u32(St + s * 4 * T64), 16, 1024, kLayoutSw128);
+            const uint64_t dd = desc_advance(qd, T64);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 64, make_smem_desc(ka + offa, 16, 1024, kLayoutSw128),
-                           make_smem_desc(qa + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+              umma_tf32<1>(tmem_base + s * 64, desc_advance(kd, offa), desc_advance(qd, offb), idesc_s, k != 0);
             }
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + 128 + s * 64, make_smem_desc(va + offa, 16, 1024, kLayoutSw128),
-                           make_smem_desc(da + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+              umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(vd, offa), desc_advance(dd, offb), idesc_s, k != 0);
             }
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&qk_empty[s]);
@@ -444,15 +443,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
             mbar_wait(&qm_full[s], (dv_it >> 1) & 1);
             if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
             tcgen05_fence_after();
-            const uint32_t qm = smem_u32(St + s * 4 * T64 + 2 * T64), dm = qm + T64;
+            const uint64_t qmd = make_smem_desc(smem_u32(St + s * 4 * T64 + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+            const uint64_t dmd = desc_advance(qmd, T64);
+            const uint32_t acc_on = i > 1;
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // dV += P^T dO
-              umma_tf32_ts(tmem_base + 256, tmem_base + s * 64 + k * 8,
-                           make_smem_desc(dm + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+              umma_tf32_ts(tmem_base + 256, tmem_base + s * 64 + k * 8, desc_advance(dmd, k * 1024), idesc_g, acc_on | (k != 0));
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // dK += dS^T Q
-              umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8,
-                           make_smem_desc(qm + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+              umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8, desc_advance(qmd, k * 1024), idesc_g, acc_on | (k != 0));
             umma_commit<1>(&qm_empty[s]);
             if (i == NS) umma_commit<1>(acc_full);
             ++dv_it;
@@ -616,14 +615,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
           const int s = sub_it & 1;
           const uint32_t ph = (sub_it >> 1) & 1;
           uint8_t* st = St + s * 3 * T64;
+          DBG_T(p0);
           mbar_wait(&kk_empty[s], ph ^ 1);
+          DBG_T(p1);
+          if (blockIdx.x == 0) g_attn_dbg[0] += p1 - p0;
           mbar_arrive_expect_tx(&kk_full[s], 2 * T64);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             tma_load_3d(st + kb * KBLK64, &tmKV64, &kk_full[s], inner + h * DH + kb * 32, i * 64, b);
             tma_load_3d(st + T64 + kb * KBLK64, &tmKV64, &kk_full[s], 2 * inner + h * DH + kb * 32, i * 64, b);
           }
+          DBG_T(p2);
           mbar_wait(&km_empty[s], ph ^ 1);
+          DBG_T(p3);
+          if (blockIdx.x == 0) g_attn_dbg[1] += p3 - p2;
           mbar_arrive_expect_tx(&km_full[s], T64);
           tma_load_4d(st + 2 * T64, &tmKM, &km_full[s], 0, i * 64, (inner + h * DH) / 32, b);
         }
@@ -637,24 +642,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
         mbar_wait(q_full, item_it & 1);
         tcgen05_fence_after();
-        const uint32_t qa = smem_u32(Qs), da = smem_u32(Ds);
+        const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+        const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
         for (int i = 0; i <= NS; ++i) {
           if (i < NS) {
             const int s = sd_it & 1;
+            DBG_T(m0);
             mbar_wait(&kk_full[s], (sd_it >> 1) & 1);
+            DBG_T(m1);
+            if (blockIdx.x == 0) g_attn_dbg[2] += m1 - m0;
             tcgen05_fence_after();
-            const uint32_t kk = smem_u32(St + s * 3 * T64), vk = kk + T64;
+            const uint64_t kkd = make_smem_desc(smem_u32(St + s * 3 * T64), 16, 1024, kLayoutSw128);
+            const uint64_t vkd = desc_advance(kkd, T64);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 64, make_smem_desc(qa + offa, 16, 1024, kLayoutSw128),
-                           make_smem_desc(kk + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+              umma_tf32<1>(tmem_base + s * 64, desc_advance(qd, offa), desc_advance(kkd, offb), idesc_s, k != 0);
             }
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + 128 + s * 64, make_smem_desc(da + offa, 16, 1024, kLayoutSw128),
-                           make_smem_desc(vk + offb, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+              umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(dd, offa), desc_advance(vkd, offb), idesc_s, k != 0);
             }
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&kk_empty[s]);
@@ -663,17 +671,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
           }
           if (i >= 1) {
             const int s = dq_it & 1;
+            DBG_T(m2);
             mbar_wait(&p_full[s], (dq_it >> 1) & 1);
+            DBG_T(m3);
             mbar_wait(&km_full[s], (dq_it >> 1) & 1);
+            DBG_T(m4);
             if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+            DBG_T(m5);
+            if (blockIdx.x == 0) { g_attn_dbg[3] += m3 - m2; g_attn_dbg[4] += m4 - m3; g_attn_dbg[5] += m5 - m4; }
             tcgen05_fence_after();
-            const uint32_t km = smem_u32(St + s * 3 * T64 + 2 * T64);
+            const uint64_t kmd = make_smem_desc(smem_u32(St + s * 3 * T64 + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+            const uint32_t acc_on = i > 1;
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // dQ += dS K
-              umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8,
-                           make_smem_desc(km + k * 1024, KBLK64, 512, kLayoutSw128Base32), idesc_g, (i > 1) || (k != 0));
+              umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
             umma_commit<1>(&km_empty[s]);
             if (i == NS) umma_commit<1>(acc_full);
+            if (blockIdx.x == 0) { g_attn_dbg[6] += clock64() - m5; g_attn_dbg[7] += 1; }
             ++dq_it;
           }
         }
@@ -696,7 +710,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
+        const bool dbg = blockIdx.x == 0 && threadIdx.x == 64;
+        DBG_T(s0);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        DBG_T(s1);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
         const int kv_left = p.N - i * 64 - half * 32;
@@ -704,16 +721,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
+        DBG_T(s2);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
           g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
         }
+        DBG_T(s3);
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
+        DBG_T(s4);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (dbg) {
+          g_attn_dbg[8] += s1 - s0; g_attn_dbg[9] += s2 - s1; g_attn_dbg[10] += s3 - s2; g_attn_dbg[11] += s4 - s3;
+          g_attn_dbg[12] += clock64() - s4; g_attn_dbg[13] += 1;
+        }
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -794,6 +818,15 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
   k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, p);
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
+  return 0;
+}
+
+int debug_counters(long long* out, int n, int reset) {
+  long long h[32] = {0};
+  if (n > 32) n = 32;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(h, g_attn_dbg, sizeof(h)));
+  for (int i = 0; i < n; ++i) out[i] = h[i];
+  if (reset) { long long z[32] = {0}; B200_CUDA_OK(cudaMemcpyToSymbol(g_attn_dbg, z, sizeof(z))); }
   return 0;
 }
 

@@ -279,6 +279,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)layout << 61;
   return d;
 }
+// advance the start-address field of a descriptor by a byte offset (no carry out of the 14-bit
+// field as long as the operand stays inside the 227 KB window): one 64-bit add instead of
+// re-encoding -- the single MMA-issuing thread cannot hide ALU latency behind other warps
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); }
 // instruction descriptor for kind::tf32, fp32 accumulate (upper 32 bits of the 64-bit idesc):
 //   [4,6) c_format=1(F32)  [7,10) a_format=2(TF32)  [10,13) b_format=2  [15] a_major  [16] b_major
 //   [17,23) N>>3  [24,29) M>>4

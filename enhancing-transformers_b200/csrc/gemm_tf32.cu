@@ -157,6 +157,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t A_SBO = AMAJ ? 512 : 1024, B_SBO = BMAJ ? 512 : 1024;
       constexpr uint32_t A_LAY = AMAJ ? kLayoutSw128Base32 : kLayoutSw128, B_LAY = BMAJ ? kLayoutSw128Base32 : kLayoutSw128;
       constexpr uint32_t A_KSTEP = AMAJ ? 1024 : 32, B_KSTEP = BMAJ ? 1024 : 32;  // bytes per UMMA_K = 8
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), A_LBO, A_SBO, A_LAY);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + Cfg::A_BYTES, B_LBO, B_SBO, B_LAY);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -169,14 +171,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t ad = desc_advance(a_desc0, stage * Cfg::STAGE_BYTES);
+          const uint64_t bd = desc_advance(b_desc0, stage * Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * A_KSTEP, A_LBO, A_SBO, A_LAY);
-            const uint64_t bd = make_smem_desc(sb + k * B_KSTEP, B_LBO, B_SBO, B_LAY);
-            umma_tf32<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kBK / 8; ++k)
+            umma_tf32<CG>(d_tmem, desc_advance(ad, k * A_KSTEP), desc_advance(bd, k * B_KSTEP), idesc, (kb | k) != 0);
           umma_commit<CG>(&empty_bar[stage]);  // frees the slot in both CTAs once the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

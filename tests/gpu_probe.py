@@ -392,6 +392,32 @@ def g_precision():
         etb.functional.clear_shadow_cache(); torch.cuda.empty_cache()
 
 
+def g_attn_dbg():
+    import ctypes
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    L = etb._lib.lib()
+    B, N, heads, dh = 32, 1024, 12, 64
+    inner = heads * dh
+    qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
+    o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
+    do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
+    buf = (ctypes.c_longlong * 32)()
+    ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
+    torch.cuda.synchronize()
+    L.b200vq_debug_counters(buf, 32, 1)
+    ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
+    torch.cuda.synchronize()
+    L.b200vq_debug_counters(buf, 32, 1)
+    v = list(buf)
+    n_mma, n_sm = max(v[7], 1), max(v[13], 1)
+    print("dq kernel block 0, cycles per sub-tile:")
+    print(f"  producer: wait kk_empty {v[0]/n_mma:.0f}  wait km_empty {v[1]/n_mma:.0f}")
+    print(f"  mma: wait kk_full {v[2]/n_mma:.0f}  wait p_full {v[3]/n_mma:.0f}  wait km_full {v[4]/n_mma:.0f}  wait acc_empty {v[5]/n_mma:.0f}  issue dQ {v[6]/n_mma:.0f}   (n={n_mma})")
+    print(f"  softmax: wait s_full {v[8]/n_sm:.0f}  tmem ld {v[9]/n_sm:.0f}  compute {v[10]/n_sm:.0f}  tmem st {v[11]/n_sm:.0f}  arrive {v[12]/n_sm:.0f}  (n={n_sm})")
+
+
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
 
 if __name__ == "__main__":
