@@ -36,7 +36,6 @@ _SIGNATURES = {
     "b200vq_colsum": (c_i, [c_f, c_ll, c_i, c_i, c_f, c_f, c_sz, c_f]),
     "b200vq_round_tf32": (c_i, [c_f, c_f, c_ll, c_f]),
     "b200vq_add_rows_mod": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_f]),
-    "b200vq_debug_counters": (c_i, [ctypes.POINTER(ctypes.c_longlong), c_i, c_i]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

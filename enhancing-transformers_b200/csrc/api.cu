@@ -55,7 +55,6 @@ size_t colsum_workspace_bytes(int);
 int colsum(const float*, long long, int, int, float*, void*, size_t, cudaStream_t);
 int round_tf32_copy(const float*, float*, long long, cudaStream_t);
 int add_rows_mod(const float*, const float*, float*, long long, int, int, cudaStream_t);
-int debug_counters(long long*, int, int);
 
 }  // namespace b200
 
@@ -124,7 +123,5 @@ int b200vq_round_tf32(const float* in, float* out, long long n, void* stream) { 
 int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream) {
   return add_rows_mod(x, table, out, M, D, R, S(stream));
 }
-
-int b200vq_debug_counters(long long* out, int n, int reset) { return debug_counters(out, n, reset); }
 
 }  // extern "C"

@@ -83,48 +83,56 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const int T = p.kv_tiles;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t kv_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        const int qt = w % p.q_tiles;
-        const int bh = w / p.q_tiles;
-        const int h = bh % p.heads, b = bh / p.heads;
-        mbar_wait(q_empty, (item_it & 1) ^ 1);
+    // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
+    uint32_t kv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(q_full, TILE_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) tma_load_3d(Qs + kb * KBLK_BYTES, &tmQK, q_full, h * DH + kb * 32, qt * 128, b);
-        for (int j = 0; j < T; ++j, ++kv_it) {
-          const int s = kv_it & 1;
-          const uint32_t ph = (kv_it >> 1) & 1;
-          mbar_wait(&k_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int s = kv_it & 1;
+        const uint32_t ph = (kv_it >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
             tma_load_3d(Ks + s * TILE_BYTES + kb * KBLK_BYTES, &tmQK, &k_full[s], inner + h * DH + kb * 32, j * 128, b);
-          mbar_wait(&v_empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
           tma_load_4d(Vs + s * TILE_BYTES, &tmV, &v_full[s], 0, j * 128, (2 * inner + h * DH) / 32, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // S = Q K^T, both K-major
-      constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // O = P V, B MN-major
-      uint32_t s_it = 0, pv_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        mbar_wait(q_full, item_it & 1);
-        tcgen05_fence_after();
-        const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
-        for (int j = 0; j <= T; ++j) {
-          if (j < T) {
-            const int s = s_it & 1;
-            const uint32_t ph = (s_it >> 1) & 1;
-            mbar_wait(&k_full[s], ph);
-            tcgen05_fence_after();
-            const uint64_t kd = make_smem_desc(smem_u32(Ks + s * TILE_BYTES), 16, 1024, kLayoutSw128);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // S = Q K^T, both K-major
+    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // O = P V, B MN-major
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+    const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
+    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
+    uint32_t s_it = 0, pv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      tcgen05_fence_after();
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {
+          const int s = s_it & 1;
+          mbar_wait(&k_full[s], (s_it >> 1) & 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t kd = desc_advance(kd0, s * TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
               const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
@@ -133,23 +141,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&k_empty[s]);
             if (j == T - 1) umma_commit<1>(q_empty);
-            ++s_it;
           }
-          if (j >= 1) {
-            const int s = pv_it & 1;
-            const uint32_t ph = (pv_it >> 1) & 1;
-            mbar_wait(&p_full[s], ph);
-            mbar_wait(&v_full[s], ph);
-            mbar_wait(&o_empty[s], ph ^ 1);
-            tcgen05_fence_after();
-            const uint64_t vd = make_smem_desc(smem_u32(Vs + s * TILE_BYTES), KBLK_BYTES, 512, kLayoutSw128Base32);
+          __syncwarp();
+          ++s_it;
+        }
+        if (j >= 1) {
+          const int s = pv_it & 1;
+          const uint32_t ph = (pv_it >> 1) & 1;
+          mbar_wait(&p_full[s], ph);
+          mbar_wait(&v_full[s], ph);
+          mbar_wait(&o_empty[s], ph ^ 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               umma_tf32_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, k != 0);
             umma_commit<1>(&o_full[s]);
             umma_commit<1>(&v_empty[s]);
-            ++pv_it;
           }
+          __syncwarp();
+          ++pv_it;
         }
       }
     }
@@ -309,9 +321,6 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
 // Q / dO (resp. K) are needed both as K-major operands (SWIZZLE_128B) and as MN-major operands
 // (SWIZZLE_128B_BASE32B): TMA fetches the same global tile twice with two tensor maps.
 // =============================================================================================
-// cycle counters of block 0 (development aid, read back with b200vq_debug_counters): filled only by the dQ kernel
-__device__ long long g_attn_dbg[32];
-#define DBG_T(var) const long long var = clock64()
 
 struct AttnBwdParams {
   const float* lse;     // [B*heads*N]
@@ -374,53 +383,62 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   const int NS = p.sub64;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t sub_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        const int kt = w % p.tiles128;
-        const int bh = w / p.tiles128;
-        const int h = bh % p.heads, b = bh / p.heads;
-        mbar_wait(kv_empty, (item_it & 1) ^ 1);
+    uint32_t sub_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int kt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(kv_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full, 2 * T128);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           tma_load_3d(Ks + kb * KBLK128, &tmKV, kv_full, inner + h * DH + kb * 32, kt * 128, b);
           tma_load_3d(Vs + kb * KBLK128, &tmKV, kv_full, 2 * inner + h * DH + kb * 32, kt * 128, b);
         }
-        for (int i = 0; i < NS; ++i, ++sub_it) {
-          const int s = sub_it & 1;
-          const uint32_t ph = (sub_it >> 1) & 1;
-          uint8_t* st = St + s * 4 * T64;
-          mbar_wait(&qk_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      for (int i = 0; i < NS; ++i, ++sub_it) {
+        const int s = sub_it & 1;
+        const uint32_t ph = (sub_it >> 1) & 1;
+        uint8_t* st = St + s * 4 * T64;
+        mbar_wait(&qk_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&qk_full[s], 2 * T64);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             tma_load_3d(st + kb * KBLK64, &tmQ64, &qk_full[s], h * DH + kb * 32, i * 64, b);
             tma_load_3d(st + T64 + kb * KBLK64, &tmDO64, &qk_full[s], h * DH + kb * 32, i * 64, b);
           }
-          mbar_wait(&qm_empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        mbar_wait(&qm_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&qm_full[s], 2 * T64);
           tma_load_4d(st + 2 * T64, &tmQM, &qm_full[s], 0, i * 64, (h * DH) / 32, b);
           tma_load_4d(st + 3 * T64, &tmDOM, &qm_full[s], 0, i * 64, (h * DH) / 32, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
-      constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
-      uint32_t sd_it = 0, dv_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        mbar_wait(kv_full, item_it & 1);
-        tcgen05_fence_after();
-        const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
-        const uint64_t vd = make_smem_desc(smem_u32(Vs), 16, 1024, kLayoutSw128);
-        for (int i = 0; i <= NS; ++i) {
-          if (i < NS) {
-            const int s = sd_it & 1;
-            mbar_wait(&qk_full[s], (sd_it >> 1) & 1);
-            tcgen05_fence_after();
-            const uint64_t qd = make_smem_desc(smem_u32(St + s * 4 * T64), 16, 1024, kLayoutSw128);
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
+    const uint64_t vd = make_smem_desc(smem_u32(Vs), 16, 1024, kLayoutSw128);
+    const uint64_t qd0 = make_smem_desc(smem_u32(St), 16, 1024, kLayoutSw128);
+    const uint64_t qmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+    uint32_t sd_it = 0, dv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(kv_full, item_it & 1);
+      tcgen05_fence_after();
+      for (int i = 0; i <= NS; ++i) {
+        if (i < NS) {
+          const int s = sd_it & 1;
+          mbar_wait(&qk_full[s], (sd_it >> 1) & 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t qd = desc_advance(qd0, s * 4 * T64);
             const uint64_t dd = desc_advance(qd, T64);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
@@ -435,15 +453,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&qk_empty[s]);
             if (i == NS - 1) umma_commit<1>(kv_empty);
-            ++sd_it;
           }
-          if (i >= 1) {
-            const int s = dv_it & 1;
-            mbar_wait(&p_full[s], (dv_it >> 1) & 1);
-            mbar_wait(&qm_full[s], (dv_it >> 1) & 1);
-            if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-            tcgen05_fence_after();
-            const uint64_t qmd = make_smem_desc(smem_u32(St + s * 4 * T64 + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+          __syncwarp();
+          ++sd_it;
+        }
+        if (i >= 1) {
+          const int s = dv_it & 1;
+          mbar_wait(&p_full[s], (dv_it >> 1) & 1);
+          mbar_wait(&qm_full[s], (dv_it >> 1) & 1);
+          if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
             const uint64_t dmd = desc_advance(qmd, T64);
             const uint32_t acc_on = i > 1;
 #pragma unroll
@@ -454,8 +475,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
               umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8, desc_advance(qmd, k * 1024), idesc_g, acc_on | (k != 0));
             umma_commit<1>(&qm_empty[s]);
             if (i == NS) umma_commit<1>(acc_full);
-            ++dv_it;
           }
+          __syncwarp();
+          ++dv_it;
         }
       }
     }
@@ -598,61 +620,61 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   const int NS = p.sub64;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t sub_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        const int qt = w % p.tiles128;
-        const int bh = w / p.tiles128;
-        const int h = bh % p.heads, b = bh / p.heads;
-        mbar_wait(q_empty, (item_it & 1) ^ 1);
+    uint32_t sub_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(q_full, 2 * T128);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           tma_load_3d(Qs + kb * KBLK128, &tmQ128, q_full, h * DH + kb * 32, qt * 128, b);
           tma_load_3d(Ds + kb * KBLK128, &tmDO128, q_full, h * DH + kb * 32, qt * 128, b);
         }
-        for (int i = 0; i < NS; ++i, ++sub_it) {
-          const int s = sub_it & 1;
-          const uint32_t ph = (sub_it >> 1) & 1;
-          uint8_t* st = St + s * 3 * T64;
-          DBG_T(p0);
-          mbar_wait(&kk_empty[s], ph ^ 1);
-          DBG_T(p1);
-          if (blockIdx.x == 0) g_attn_dbg[0] += p1 - p0;
+      }
+      __syncwarp();
+      for (int i = 0; i < NS; ++i, ++sub_it) {
+        const int s = sub_it & 1;
+        const uint32_t ph = (sub_it >> 1) & 1;
+        uint8_t* st = St + s * 3 * T64;
+        mbar_wait(&kk_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&kk_full[s], 2 * T64);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             tma_load_3d(st + kb * KBLK64, &tmKV64, &kk_full[s], inner + h * DH + kb * 32, i * 64, b);
             tma_load_3d(st + T64 + kb * KBLK64, &tmKV64, &kk_full[s], 2 * inner + h * DH + kb * 32, i * 64, b);
           }
-          DBG_T(p2);
-          mbar_wait(&km_empty[s], ph ^ 1);
-          DBG_T(p3);
-          if (blockIdx.x == 0) g_attn_dbg[1] += p3 - p2;
+        }
+        __syncwarp();
+        mbar_wait(&km_empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&km_full[s], T64);
           tma_load_4d(st + 2 * T64, &tmKM, &km_full[s], 0, i * 64, (inner + h * DH) / 32, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
-      constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
-      uint32_t sd_it = 0, dq_it = 0, item_it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-        mbar_wait(q_full, item_it & 1);
-        tcgen05_fence_after();
-        const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
-        const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
-        for (int i = 0; i <= NS; ++i) {
-          if (i < NS) {
-            const int s = sd_it & 1;
-            DBG_T(m0);
-            mbar_wait(&kk_full[s], (sd_it >> 1) & 1);
-            DBG_T(m1);
-            if (blockIdx.x == 0) g_attn_dbg[2] += m1 - m0;
-            tcgen05_fence_after();
-            const uint64_t kkd = make_smem_desc(smem_u32(St + s * 3 * T64), 16, 1024, kLayoutSw128);
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+    const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
+    const uint64_t kkd0 = make_smem_desc(smem_u32(St), 16, 1024, kLayoutSw128);
+    const uint64_t kmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+    uint32_t sd_it = 0, dq_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      tcgen05_fence_after();
+      for (int i = 0; i <= NS; ++i) {
+        if (i < NS) {
+          const int s = sd_it & 1;
+          mbar_wait(&kk_full[s], (sd_it >> 1) & 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t kkd = desc_advance(kkd0, s * 3 * T64);
             const uint64_t vkd = desc_advance(kkd, T64);
 #pragma unroll
             for (int k = 0; k < DH / 8; ++k) {
@@ -667,29 +689,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
             umma_commit<1>(&s_full[s]);
             umma_commit<1>(&kk_empty[s]);
             if (i == NS - 1) umma_commit<1>(q_empty);
-            ++sd_it;
           }
-          if (i >= 1) {
-            const int s = dq_it & 1;
-            DBG_T(m2);
-            mbar_wait(&p_full[s], (dq_it >> 1) & 1);
-            DBG_T(m3);
-            mbar_wait(&km_full[s], (dq_it >> 1) & 1);
-            DBG_T(m4);
-            if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-            DBG_T(m5);
-            if (blockIdx.x == 0) { g_attn_dbg[3] += m3 - m2; g_attn_dbg[4] += m4 - m3; g_attn_dbg[5] += m5 - m4; }
-            tcgen05_fence_after();
-            const uint64_t kmd = make_smem_desc(smem_u32(St + s * 3 * T64 + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+          __syncwarp();
+          ++sd_it;
+        }
+        if (i >= 1) {
+          const int s = dq_it & 1;
+          mbar_wait(&p_full[s], (dq_it >> 1) & 1);
+          mbar_wait(&km_full[s], (dq_it >> 1) & 1);
+          if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t kmd = desc_advance(kmd0, s * 3 * T64);
             const uint32_t acc_on = i > 1;
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // dQ += dS K
               umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
             umma_commit<1>(&km_empty[s]);
             if (i == NS) umma_commit<1>(acc_full);
-            if (blockIdx.x == 0) { g_attn_dbg[6] += clock64() - m5; g_attn_dbg[7] += 1; }
-            ++dq_it;
           }
+          __syncwarp();
+          ++dq_it;
         }
       }
     }
@@ -710,10 +730,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
-        const bool dbg = blockIdx.x == 0 && threadIdx.x == 64;
-        DBG_T(s0);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
-        DBG_T(s1);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
         const int kv_left = p.N - i * 64 - half * 32;
@@ -721,23 +738,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        DBG_T(s2);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
           g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
         }
-        DBG_T(s3);
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
-        DBG_T(s4);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
-        if (dbg) {
-          g_attn_dbg[8] += s1 - s0; g_attn_dbg[9] += s2 - s1; g_attn_dbg[10] += s3 - s2; g_attn_dbg[11] += s4 - s3;
-          g_attn_dbg[12] += clock64() - s4; g_attn_dbg[13] += 1;
-        }
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -818,15 +828,6 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
   k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, p);
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
-  return 0;
-}
-
-int debug_counters(long long* out, int n, int reset) {
-  long long h[32] = {0};
-  if (n > 32) n = 32;
-  B200_CUDA_OK(cudaMemcpyFromSymbol(h, g_attn_dbg, sizeof(h)));
-  for (int i = 0; i < n; ++i) out[i] = h[i];
-  if (reset) { long long z[32] = {0}; B200_CUDA_OK(cudaMemcpyToSymbol(g_attn_dbg, z, sizeof(z))); }
   return 0;
 }
 

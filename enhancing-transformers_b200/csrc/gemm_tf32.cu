@@ -109,19 +109,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_clusters = gridDim.x / CG;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int z = t / tiles_per_split;
-        const int r = t - z * tiles_per_split;
-        const int mb = r / p.num_n_blocks, nb = r - mb * p.num_n_blocks;
-        const int m0 = (mb * CG + (int)cta_rank) * kBM;
-        const int n0 = nb * BN + (int)cta_rank * Cfg::BN_CTA;
-        const int kbase = z * p.K;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ---------------------------------------------------------------- TMA producer (warp-uniform loop, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      const int z = t / tiles_per_split;
+      const int r = t - z * tiles_per_split;
+      const int mb = r / p.num_n_blocks, nb = r - mb * p.num_n_blocks;
+      const int m0 = (mb * CG + (int)cta_rank) * kBM;
+      const int n0 = nb * BN + (int)cta_rank * Cfg::BN_CTA;
+      const int kbase = z * p.K;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = kbase + kb * kBK;
@@ -142,13 +142,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (BMAJ == 0) tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, n0);
             else                     tma_load_3d_2sm(sb, &tmB, &full_bar[stage], 0, k0, n0 / 32);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (leader && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM * CG, BN, AMAJ, BMAJ);
       // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), LBO unused.
       // MN-major (SWIZZLE_128B_BASE32B, mandatory for tf32): smem holds [mn atom of 32][32 k-rows][128 B];
@@ -171,15 +172,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t ad = desc_advance(a_desc0, stage * Cfg::STAGE_BYTES);
-          const uint64_t bd = desc_advance(b_desc0, stage * Cfg::STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t ad = desc_advance(a_desc0, stage * Cfg::STAGE_BYTES);
+            const uint64_t bd = desc_advance(b_desc0, stage * Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k)
-            umma_tf32<CG>(d_tmem, desc_advance(ad, k * A_KSTEP), desc_advance(bd, k * B_KSTEP), idesc, (kb | k) != 0);
-          umma_commit<CG>(&empty_bar[stage]);  // frees the slot in both CTAs once the MMAs retire
+            for (int k = 0; k < kBK / 8; ++k)
+              umma_tf32<CG>(d_tmem, desc_advance(ad, k * A_KSTEP), desc_advance(bd, k * B_KSTEP), idesc, (kb | k) != 0);
+            umma_commit<CG>(&empty_bar[stage]);  // frees the slot in both CTAs once the MMAs retire
+            if (kb == p.k_blocks - 1) umma_commit<CG>(&tmem_full[acc]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit<CG>(&tmem_full[acc]);
       }
     }
   } else {

@@ -102,9 +102,6 @@ int b200vq_round_tf32(const float* in, float* out, long long n, void* stream);
 /* out[m,:] = x[m,:] + table[m % R,:]  (token + de_pos_embedding, layers.py:210) */
 int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream);
 
-/* development aid: cycle counters recorded by block 0 of the attention backward kernels (host array out[n<=32]) */
-int b200vq_debug_counters(long long* out, int n, int reset);
-
 #ifdef __cplusplus
 }
 #endif

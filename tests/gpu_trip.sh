@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 200 python tests/gpu_probe.py attention 2>&1 | tail -9
-timeout 200 python tests/gpu_probe.py attn_dbg 2>&1 | tail -5
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
 timeout 200 python tests/gpu_probe.py gemm_perf 2>&1 | grep -E "cg=2 bn=256|cuBLAS|dgrad cg=2|wgrad cg=2 splits=4"
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
