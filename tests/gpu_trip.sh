@@ -1,6 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 python tests/gpu_probe.py attention 2>&1 | tail -9
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-timeout 200 python tests/gpu_probe.py gemm_perf 2>&1 | grep -E "cg=2 bn=256|cuBLAS|dgrad cg=2|wgrad cg=2 splits=4"
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
+nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|Thread|Core" | head -6
+python - <<'PY'
+import time, torch, sys, os
+sys.path.insert(0, os.getcwd())
+from bench import oracle_step
+for thr in (8, 16, 32, 64):
+    step = oracle_step("base", 2, thr)
+    t0 = time.time(); s = step(); 
+    print(f"threads={thr}: base B=2 fwd+bwd {s:.1f}s -> {2/s:.3f} img/s", flush=True)
+PY
