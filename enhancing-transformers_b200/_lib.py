@@ -6,7 +6,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vq.so")
+LIB_PATH = os.environ.get("B200VQ_LIB") or os.path.join(_HERE, "libb200vq.so")   # B200VQ_LIB: development builds (trace hooks)
 _lock = threading.Lock()
 _lib = None
 

@@ -1,5 +1,10 @@
 // tcgen05 / TMEM flash-attention forward for the ViT blocks (reference layers.py:124-130).
 //
+// Two MMA-issuing warps: tcgen05.mma issue blocks while the tensor pipe executes (measured: the
+// queue is one or two instructions deep), so a single issuer serialises its own mbarrier polling
+// (~100 cycles per wait) with MMA execution.  Issuer A (warp 1) issues the score-type MMAs, issuer
+// B (warp 10) the P.V-type MMAs; cross-issuer hazards are covered by mbarriers (sfree).
+//
 // Persistent, warp-specialised, one work item = (batch, head, 128-query tile):
 //   warp 0      TMA producer: Q tile once per item, K and V tiles (128 keys) through 2-stage rings.
 //               q/k are K-major operands (SWIZZLE_128B, one 128-byte block per 32 head dims);
@@ -16,7 +21,31 @@
 
 namespace b200 {
 
-constexpr int kAtcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
+// Development trace (compiled only with -DB200_ATTN_TRACE into a separate .so): block 0 of the dQ
+// kernel logs (event id, clock64) pairs of its MMA warp and of one softmax warp.
+#ifdef B200_ATTN_TRACE
+__device__ long long g_trace[3 * 2048];
+// per-role trace rings in shared memory (no atomics, ~10 cycles per event); role r logs (event, clock) pairs
+#define TRACE_DECL __shared__ long long tr_buf[3][2048]; int tr_n = 0
+#define TRACE(role, ev)                                                                           \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 1023) {                              \
+      tr_buf[role][2 * tr_n] = (ev); tr_buf[role][2 * tr_n + 1] = clock64(); ++tr_n;             \
+    }                                                                                             \
+  } while (0)
+#define TRACE_DUMP()                                                                              \
+  do {                                                                                            \
+    __syncthreads();                                                                              \
+    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 2048; i_ += blockDim.x) g_trace[i_] = tr_buf[i_ / 2048][i_ % 2048]; \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(role, ev) do {} while (0)
+#define TRACE_DUMP() do {} while (0)
+#endif
+
+constexpr int kAtcThreads = 352;      // warp 0 TMA, warp 1 MMA issuer A, warps 2..9 softmax (two per TMEM lane quarter), warp 10 MMA issuer B
+constexpr int kIssuerB = 10;
 constexpr int kAtcSoftmaxThreads = 256;
 
 template <int NC>
@@ -57,8 +86,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   uint64_t* p_full = bars + 12;   // [2]
   uint64_t* o_full = bars + 14;   // [2]
   uint64_t* o_empty = bars + 16;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* xch = reinterpret_cast<float*>(bars + 20);   // [3][2][128] row-max (double buffered) and row-sum exchange
+  uint64_t* sfree = bars + 18;    // [2] S/P buffer consumed by the P.V MMAs (issuer B -> issuer A)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -71,6 +101,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
       mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
+      mbar_init(&sfree[s], 1);
     }
     fence_barrier_init();
   }
@@ -116,53 +147,56 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
-    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // S = Q K^T, both K-major
-    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // O = P V, B MN-major
+    // ------------------------------------------------------------------ MMA issuer A: S_j = Q K_j^T
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // both operands K-major
     const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
     const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
-    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
-    uint32_t s_it = 0, pv_it = 0, item_it = 0;
+    uint32_t s_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       mbar_wait(q_full, item_it & 1);
-      tcgen05_fence_after();
-      for (int j = 0; j <= T; ++j) {
-        if (j < T) {
-          const int s = s_it & 1;
-          mbar_wait(&k_full[s], (s_it >> 1) & 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t kd = desc_advance(kd0, s * TILE_BYTES);
+      for (int j = 0; j < T; ++j, ++s_it) {
+        const int s = s_it & 1;
+        const uint32_t ph = (s_it >> 1) & 1;
+        mbar_wait(&k_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);       // P_{j-2} (same buffer) has been consumed by issuer B
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = desc_advance(kd0, s * TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < DH / 8; ++k) {
-              const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
-            }
-            umma_commit<1>(&s_full[s]);
-            umma_commit<1>(&k_empty[s]);
-            if (j == T - 1) umma_commit<1>(q_empty);
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + s * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
           }
-          __syncwarp();
-          ++s_it;
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&k_empty[s]);
+          if (j == T - 1) umma_commit<1>(q_empty);
         }
-        if (j >= 1) {
-          const int s = pv_it & 1;
-          const uint32_t ph = (pv_it >> 1) & 1;
-          mbar_wait(&p_full[s], ph);
-          mbar_wait(&v_full[s], ph);
-          mbar_wait(&o_empty[s], ph ^ 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ------------------------------------------------------------------ MMA issuer B: O_j = P_j V_j (A operand from TMEM)
+    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // B MN-major
+    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
+    uint32_t pv_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      for (int j = 0; j < T; ++j, ++pv_it) {
+        const int s = pv_it & 1;
+        const uint32_t ph = (pv_it >> 1) & 1;
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&o_empty[s], ph ^ 1);
+        mbar_wait(&p_full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              umma_tf32_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, k != 0);
-            umma_commit<1>(&o_full[s]);
-            umma_commit<1>(&v_empty[s]);
-          }
-          __syncwarp();
-          ++pv_it;
+          for (int k = 0; k < 16; ++k)
+            umma_tf32_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, k != 0);
+          umma_commit<1>(&o_full[s]);
+          umma_commit<1>(&v_empty[s]);
+          umma_commit<1>(&sfree[s]);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -297,7 +331,7 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 256 + 3 * 256 * 4;
+  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 512 + 3 * 256 * 4;
   auto kern = attn_fwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
@@ -359,10 +393,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint64_t* p_full = bars + 12;    // [2]
   uint64_t* acc_full = bars + 14;
   uint64_t* acc_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* sfree = bars + 16;     // [2] P^T / dS^T buffers consumed by issuer B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
+    mbar_init(&sfree[0], 1); mbar_init(&sfree[1], 1);
     tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmDO64);
     tma_prefetch_desc(&tmQM); tma_prefetch_desc(&tmDOM);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
@@ -422,63 +458,68 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       }
     }
   } else if (warp == 1) {
+    // ---- issuer A: S^T = K Q^T, dP^T = V dO^T
     constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
-    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
     const uint64_t kd = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
     const uint64_t vd = make_smem_desc(smem_u32(Vs), 16, 1024, kLayoutSw128);
     const uint64_t qd0 = make_smem_desc(smem_u32(St), 16, 1024, kLayoutSw128);
-    const uint64_t qmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
-    uint32_t sd_it = 0, dv_it = 0, item_it = 0;
+    uint32_t sd_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       mbar_wait(kv_full, item_it & 1);
-      tcgen05_fence_after();
-      for (int i = 0; i <= NS; ++i) {
-        if (i < NS) {
-          const int s = sd_it & 1;
-          mbar_wait(&qk_full[s], (sd_it >> 1) & 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t qd = desc_advance(qd0, s * 4 * T64);
-            const uint64_t dd = desc_advance(qd, T64);
+      for (int i = 0; i < NS; ++i, ++sd_it) {
+        const int s = sd_it & 1;
+        const uint32_t ph = (sd_it >> 1) & 1;
+        mbar_wait(&qk_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t qd = desc_advance(qd0, s * 4 * T64);
+          const uint64_t dd = desc_advance(qd, T64);
 #pragma unroll
-            for (int k = 0; k < DH / 8; ++k) {
-              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 64, desc_advance(kd, offa), desc_advance(qd, offb), idesc_s, k != 0);
-            }
-#pragma unroll
-            for (int k = 0; k < DH / 8; ++k) {
-              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(vd, offa), desc_advance(dd, offb), idesc_s, k != 0);
-            }
-            umma_commit<1>(&s_full[s]);
-            umma_commit<1>(&qk_empty[s]);
-            if (i == NS - 1) umma_commit<1>(kv_empty);
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + s * 64, desc_advance(kd, offa), desc_advance(qd, offb), idesc_s, k != 0);
           }
-          __syncwarp();
-          ++sd_it;
-        }
-        if (i >= 1) {
-          const int s = dv_it & 1;
-          mbar_wait(&p_full[s], (dv_it >> 1) & 1);
-          mbar_wait(&qm_full[s], (dv_it >> 1) & 1);
-          if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
-            const uint64_t dmd = desc_advance(qmd, T64);
-            const uint32_t acc_on = i > 1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)   // dV += P^T dO
-              umma_tf32_ts(tmem_base + 256, tmem_base + s * 64 + k * 8, desc_advance(dmd, k * 1024), idesc_g, acc_on | (k != 0));
-#pragma unroll
-            for (int k = 0; k < 8; ++k)   // dK += dS^T Q
-              umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8, desc_advance(qmd, k * 1024), idesc_g, acc_on | (k != 0));
-            umma_commit<1>(&qm_empty[s]);
-            if (i == NS) umma_commit<1>(acc_full);
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(vd, offa), desc_advance(dd, offb), idesc_s, k != 0);
           }
-          __syncwarp();
-          ++dv_it;
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&qk_empty[s]);
+          if (i == NS - 1) umma_commit<1>(kv_empty);
         }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: dV += P^T dO, dK += dS^T Q (A operands from TMEM)
+    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t qmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+    uint32_t dv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int i = 0; i < NS; ++i, ++dv_it) {
+        const int s = dv_it & 1;
+        const uint32_t ph = (dv_it >> 1) & 1;
+        mbar_wait(&qm_full[s], ph);
+        if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        mbar_wait(&p_full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
+          const uint64_t dmd = desc_advance(qmd, T64);
+          const uint32_t acc_on = i > 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dV += P^T dO
+            umma_tf32_ts(tmem_base + 256, tmem_base + s * 64 + k * 8, desc_advance(dmd, k * 1024), idesc_g, acc_on | (k != 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dK += dS^T Q
+            umma_tf32_ts(tmem_base + 320, tmem_base + 128 + s * 64 + k * 8, desc_advance(qmd, k * 1024), idesc_g, acc_on | (k != 0));
+          umma_commit<1>(&qm_empty[s]);
+          umma_commit<1>(&sfree[s]);
+          if (i == NS - 1) umma_commit<1>(acc_full);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -589,6 +630,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 6 * T64);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
+  TRACE_DECL;
   uint64_t* kk_full = bars + 2;    // [2]
   uint64_t* kk_empty = bars + 4;   // [2]
   uint64_t* km_full = bars + 6;    // [2]
@@ -597,10 +639,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   uint64_t* p_full = bars + 12;    // [2]
   uint64_t* acc_full = bars + 14;
   uint64_t* acc_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* sfree = bars + 16;     // [2] dS buffer consumed by issuer B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
+    mbar_init(&sfree[0], 1); mbar_init(&sfree[1], 1);
     tma_prefetch_desc(&tmQ128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmKV64); tma_prefetch_desc(&tmKM);
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
@@ -658,59 +702,70 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       }
     }
   } else if (warp == 1) {
+    // ---- issuer A: S = Q K^T, dP = dO V^T
     constexpr uint32_t idesc_s = make_idesc_tf32(128, 64, 0, 0);
-    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
     const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
     const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
     const uint64_t kkd0 = make_smem_desc(smem_u32(St), 16, 1024, kLayoutSw128);
-    const uint64_t kmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
-    uint32_t sd_it = 0, dq_it = 0, item_it = 0;
+    uint32_t sd_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       mbar_wait(q_full, item_it & 1);
-      tcgen05_fence_after();
-      for (int i = 0; i <= NS; ++i) {
-        if (i < NS) {
-          const int s = sd_it & 1;
-          mbar_wait(&kk_full[s], (sd_it >> 1) & 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t kkd = desc_advance(kkd0, s * 3 * T64);
-            const uint64_t vkd = desc_advance(kkd, T64);
+      for (int i = 0; i < NS; ++i, ++sd_it) {
+        const int s = sd_it & 1;
+        const uint32_t ph = (sd_it >> 1) & 1;
+        TRACE(0, 100);
+        mbar_wait(&kk_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);
+        TRACE(0, 101);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kkd = desc_advance(kkd0, s * 3 * T64);
+          const uint64_t vkd = desc_advance(kkd, T64);
 #pragma unroll
-            for (int k = 0; k < DH / 8; ++k) {
-              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + s * 64, desc_advance(qd, offa), desc_advance(kkd, offb), idesc_s, k != 0);
-            }
-#pragma unroll
-            for (int k = 0; k < DH / 8; ++k) {
-              const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
-              umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(dd, offa), desc_advance(vkd, offb), idesc_s, k != 0);
-            }
-            umma_commit<1>(&s_full[s]);
-            umma_commit<1>(&kk_empty[s]);
-            if (i == NS - 1) umma_commit<1>(q_empty);
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + s * 64, desc_advance(qd, offa), desc_advance(kkd, offb), idesc_s, k != 0);
           }
-          __syncwarp();
-          ++sd_it;
-        }
-        if (i >= 1) {
-          const int s = dq_it & 1;
-          mbar_wait(&p_full[s], (dq_it >> 1) & 1);
-          mbar_wait(&km_full[s], (dq_it >> 1) & 1);
-          if (i == 1) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint64_t kmd = desc_advance(kmd0, s * 3 * T64);
-            const uint32_t acc_on = i > 1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)   // dQ += dS K
-              umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
-            umma_commit<1>(&km_empty[s]);
-            if (i == NS) umma_commit<1>(acc_full);
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t offa = (k >> 2) * KBLK128 + (k & 3) * 32, offb = (k >> 2) * KBLK64 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + 128 + s * 64, desc_advance(dd, offa), desc_advance(vkd, offb), idesc_s, k != 0);
           }
-          __syncwarp();
-          ++dq_it;
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&kk_empty[s]);
+          if (i == NS - 1) umma_commit<1>(q_empty);
         }
+        __syncwarp();
+        TRACE(0, 102);
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: dQ += dS K (A operand from TMEM)
+    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t kmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
+    uint32_t dq_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int i = 0; i < NS; ++i, ++dq_it) {
+        const int s = dq_it & 1;
+        const uint32_t ph = (dq_it >> 1) & 1;
+        TRACE(1, 103);
+        mbar_wait(&km_full[s], ph);
+        if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        mbar_wait(&p_full[s], ph);
+        TRACE(1, 104);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kmd = desc_advance(kmd0, s * 3 * T64);
+          const uint32_t acc_on = i > 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dQ += dS K
+            umma_tf32_ts(tmem_base + 256, tmem_base + 128 + s * 64 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
+          umma_commit<1>(&km_empty[s]);
+          umma_commit<1>(&sfree[s]);
+          if (i == NS - 1) umma_commit<1>(acc_full);
+        }
+        __syncwarp();
+        TRACE(1, 106);
       }
     }
   } else {
@@ -730,7 +785,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
+        if (warp == 2) TRACE(2, 200);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        if (warp == 2) TRACE(2, 220);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
         const int kv_left = p.N - i * 64 - half * 32;
@@ -738,16 +795,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
+        if (warp == 2) TRACE(2, 240);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
           g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
         }
+        if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (warp == 2) TRACE(2, 280);
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -771,6 +831,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       if (lane == 0) mbar_arrive(acc_empty);
     }
   }
+  TRACE_DUMP();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -830,6 +891,13 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return 0;
 }
+
+#ifdef B200_ATTN_TRACE
+extern "C" int b200vq_trace_read(long long* out) {   // out[3][2048]: (event, clock) pairs per role, zero padded
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 2048);
+  return 0;
+}
+#endif
 
 int attention_backward_tc(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B, int N,
                           int heads, int dh, float scale, int round_out, cudaStream_t stream) {

@@ -392,30 +392,40 @@ def g_precision():
         etb.functional.clear_shadow_cache(); torch.cuda.empty_cache()
 
 
-def g_attn_dbg():
+def g_attn_trace():
+    """timeline of the dQ kernel's MMA warp and two softmax warps (needs B200VQ_LIB=.../libb200vq_trace.so)"""
     import ctypes
     import torch
     import enhancing_transformers_b200 as etb
     ops = etb.ops
-    L = etb._lib.lib()
+    L = ctypes.CDLL(etb._lib.LIB_PATH)
     B, N, heads, dh = 32, 1024, 12, 64
     inner = heads * dh
     qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
     o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
     do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
-    buf = (ctypes.c_longlong * 32)()
+    buf = (ctypes.c_longlong * (3 * 2048))()
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
     torch.cuda.synchronize()
-    L.b200vq_debug_counters(buf, 32, 1)
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
     torch.cuda.synchronize()
-    L.b200vq_debug_counters(buf, 32, 1)
-    v = list(buf)
-    n_mma, n_sm = max(v[7], 1), max(v[13], 1)
-    print("dq kernel block 0, cycles per sub-tile:")
-    print(f"  producer: wait kk_empty {v[0]/n_mma:.0f}  wait km_empty {v[1]/n_mma:.0f}")
-    print(f"  mma: wait kk_full {v[2]/n_mma:.0f}  wait p_full {v[3]/n_mma:.0f}  wait km_full {v[4]/n_mma:.0f}  wait acc_empty {v[5]/n_mma:.0f}  issue dQ {v[6]/n_mma:.0f}   (n={n_mma})")
-    print(f"  softmax: wait s_full {v[8]/n_sm:.0f}  tmem ld {v[9]/n_sm:.0f}  compute {v[10]/n_sm:.0f}  tmem st {v[11]/n_sm:.0f}  arrive {v[12]/n_sm:.0f}  (n={n_sm})")
+    L.b200vq_trace_read(buf)
+    ev = []
+    for r in range(3):
+        for i in range(1024):
+            e, t = buf[r * 2048 + 2 * i], buf[r * 2048 + 2 * i + 1]
+            if t:
+                ev.append((t, r, e))
+    ev.sort()
+    t0 = ev[0][0]
+    names = {100: "wait kk_full+sfree", 101: "got them", 102: "issued S/dP", 103: "wait km_full+p_full", 104: "got them", 105: "got km_full",
+             106: "issued dQ", 200: "wait s_full", 220: "got s_full", 240: "ld done", 260: "compute done", 280: "arrived p_full"}
+    role = {0: "mmaA ", 1: "mmaB ", 2: "sm2  "}
+    start = next(i for i, (t, r, e) in enumerate(ev) if e == 100 and i > len(ev) // 2)
+    prev = ev[start][0]
+    for t, r, e in ev[start:start + 48]:
+        print(f"{t - t0:9d} (+{t - prev:5d})  {role[r]}{names.get(e, e)}")
+        prev = t
 
 
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}

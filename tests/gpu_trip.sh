@@ -1,12 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|Thread|Core" | head -6
-python - <<'PY'
-import time, torch, sys, os
-sys.path.insert(0, os.getcwd())
-from bench import oracle_step
-for thr in (8, 16, 32, 64):
-    step = oracle_step("base", 2, thr)
-    t0 = time.time(); s = step(); 
-    print(f"threads={thr}: base B=2 fwd+bwd {s:.1f}s -> {2/s:.3f} img/s", flush=True)
-PY
+timeout 200 python tests/gpu_probe.py attention 2>&1 | tail -9
+B200VQ_LIB=$PWD/enhancing-transformers_b200/libb200vq_trace.so timeout 200 python tests/gpu_probe.py attn_trace 2>&1 | tail -50
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
