@@ -24,19 +24,19 @@ namespace b200 {
 // Development trace (compiled only with -DB200_ATTN_TRACE into a separate .so): block 0 of the dQ
 // kernel logs (event id, clock64) pairs of its MMA warp and of one softmax warp.
 #ifdef B200_ATTN_TRACE
-__device__ long long g_trace[3 * 2048];
+__device__ long long g_trace[3 * 1024];
 // per-role trace rings in shared memory (no atomics, ~10 cycles per event); role r logs (event, clock) pairs
-#define TRACE_DECL __shared__ long long tr_buf[3][2048]; int tr_n = 0
+#define TRACE_DECL __shared__ long long tr_buf[3][1024]; int tr_n = 0
 #define TRACE(role, ev)                                                                           \
   do {                                                                                            \
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 1023) {                              \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 511) {                              \
       tr_buf[role][2 * tr_n] = (ev); tr_buf[role][2 * tr_n + 1] = clock64(); ++tr_n;             \
     }                                                                                             \
   } while (0)
 #define TRACE_DUMP()                                                                              \
   do {                                                                                            \
     __syncthreads();                                                                              \
-    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 2048; i_ += blockDim.x) g_trace[i_] = tr_buf[i_ / 2048][i_ % 2048]; \
+    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 1024; i_ += blockDim.x) g_trace[i_] = tr_buf[i_ / 1024][i_ % 1024]; \
   } while (0)
 #else
 #define TRACE_DECL
@@ -385,6 +385,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(Es + 128);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_empty = bars + 1;
+  TRACE_DECL;
   uint64_t* qk_full = bars + 2;    // [2]
   uint64_t* qk_empty = bars + 4;   // [2]
   uint64_t* qm_full = bars + 6;    // [2]
@@ -469,8 +470,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
         const uint32_t ph = (sd_it >> 1) & 1;
+        TRACE(0, 100);
         mbar_wait(&qk_full[s], ph);
+        TRACE(0, 107);
         mbar_wait(&sfree[s], ph ^ 1);
+        TRACE(0, 101);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qd = desc_advance(qd0, s * 4 * T64);
@@ -490,6 +494,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(kv_empty);
         }
         __syncwarp();
+        TRACE(0, 102);
       }
     }
   } else if (warp == kIssuerB) {
@@ -501,9 +506,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++dv_it) {
         const int s = dv_it & 1;
         const uint32_t ph = (dv_it >> 1) & 1;
+        TRACE(1, 103);
         mbar_wait(&qm_full[s], ph);
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        TRACE(1, 105);
         mbar_wait(&p_full[s], ph);
+        TRACE(1, 104);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
@@ -520,6 +528,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
         __syncwarp();
+        TRACE(1, 106);
       }
     }
   } else {
@@ -537,31 +546,51 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // lse / delta of a sub-tile are fetched one sub-tile ahead into registers so that the global
-      // load latency never sits between the barrier below and the score tile
-      float nl = INFINITY, ne = 0.f;                                  // +inf -> P = 0 for padded queries
-      if (et < 64 && et < p.N) { nl = lb[et] * kLog2eF; ne = eb[et]; }
+      // lse / delta of a sub-tile are fetched one sub-tile ahead into registers.  The raw loaded
+      // values are only *used* (scaled, stored to smem) at the top of the next iteration: a warp
+      // stalls at the first use of a pending load, so using them here would put the global-load
+      // latency in front of the barrier every sub-tile.
+      float nl = 0.f, ne = 0.f;
+      bool nvalid = et < 64 && et < p.N;
+      if (nvalid) { nl = lb[et]; ne = eb[et]; }
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
         if (et < 64) {
-          Ls[s * 64 + et] = nl;
-          Es[s * 64 + et] = ne;
+          Ls[s * 64 + et] = nvalid ? nl * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
+          Es[s * 64 + et] = nvalid ? ne : 0.f;
           const int qi = (i + 1) * 64 + et;
-          nl = INFINITY; ne = 0.f;
-          if (i + 1 < NS && qi < p.N) { nl = lb[qi] * kLog2eF; ne = eb[qi]; }
+          nvalid = i + 1 < NS && qi < p.N;
+          if (nvalid) { nl = lb[qi]; ne = eb[qi]; }
         }
+        if (warp == 2) TRACE(2, 199);
         softmax_bar();
+        if (warp == 2) TRACE(2, 200);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        if (warp == 2) TRACE(2, 220);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
         uint32_t v[32], g[32];
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
+        if (warp == 2) TRACE(2, 240);
+        // per-column lse / delta: read through the L1 (warp-uniform 16-byte loads) when the tile is
+        // full -- shared-memory reads here compete with the tcgen05 operand fetch of the S^T / dP^T
+        // MMAs running at the same time (measured 1700 vs ~450 cycles for this loop)
+        const bool direct = (p.N & 63) == 0;
+        const float* lq = lb + i * 64 + half * 32;
+        const float* eq = eb + i * 64 + half * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 L = *reinterpret_cast<const float4*>(&Ls[col + j]);
-          const float4 E = *reinterpret_cast<const float4*>(&Es[col + j]);
+          float4 L, E;
+          if (direct) {
+            L = __ldg(reinterpret_cast<const float4*>(lq + j));
+            E = __ldg(reinterpret_cast<const float4*>(eq + j));
+            L.x *= kLog2eF; L.y *= kLog2eF; L.z *= kLog2eF; L.w *= kLog2eF;
+          } else {
+            L = *reinterpret_cast<const float4*>(&Ls[col + j]);
+            E = *reinterpret_cast<const float4*>(&Es[col + j]);
+          }
           const float Lv[4] = {L.x, L.y, L.z, L.w}, Ev[4] = {E.x, E.y, E.z, E.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -571,12 +600,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
             g[j + u] = __float_as_uint(round_tf32(ds));
           }
         }
+        if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + col, v);
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (warp == 2) TRACE(2, 280);
       }
       // item epilogue: this thread's key row of dV (half 0) or dK (half 1)
       mbar_wait(acc_full, item_it & 1);
@@ -605,6 +636,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       if (lane == 0) mbar_arrive(acc_empty);
     }
   }
+  TRACE_DUMP();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -630,7 +662,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 6 * T64);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  TRACE_DECL;
   uint64_t* kk_full = bars + 2;    // [2]
   uint64_t* kk_empty = bars + 4;   // [2]
   uint64_t* km_full = bars + 6;    // [2]
@@ -713,10 +744,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
         const uint32_t ph = (sd_it >> 1) & 1;
-        TRACE(0, 100);
         mbar_wait(&kk_full[s], ph);
         mbar_wait(&sfree[s], ph ^ 1);
-        TRACE(0, 101);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kkd = desc_advance(kkd0, s * 3 * T64);
@@ -736,7 +765,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
           if (i == NS - 1) umma_commit<1>(q_empty);
         }
         __syncwarp();
-        TRACE(0, 102);
       }
     }
   } else if (warp == kIssuerB) {
@@ -748,11 +776,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       for (int i = 0; i < NS; ++i, ++dq_it) {
         const int s = dq_it & 1;
         const uint32_t ph = (dq_it >> 1) & 1;
-        TRACE(1, 103);
         mbar_wait(&km_full[s], ph);
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
         mbar_wait(&p_full[s], ph);
-        TRACE(1, 104);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kmd = desc_advance(kmd0, s * 3 * T64);
@@ -765,7 +791,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
         __syncwarp();
-        TRACE(1, 106);
       }
     }
   } else {
@@ -785,9 +810,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
-        if (warp == 2) TRACE(2, 200);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
-        if (warp == 2) TRACE(2, 220);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
         const int kv_left = p.N - i * 64 - half * 32;
@@ -795,19 +818,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        if (warp == 2) TRACE(2, 240);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
           g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
         }
-        if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
-        if (warp == 2) TRACE(2, 280);
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -831,7 +851,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       if (lane == 0) mbar_arrive(acc_empty);
     }
   }
-  TRACE_DUMP();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -893,8 +912,8 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
 }
 
 #ifdef B200_ATTN_TRACE
-extern "C" int b200vq_trace_read(long long* out) {   // out[3][2048]: (event, clock) pairs per role, zero padded
-  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 2048);
+extern "C" int b200vq_trace_read(long long* out) {   // out[3][1024]: (event, clock) pairs per role, zero padded
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 1024);
   return 0;
 }
 #endif

@@ -404,7 +404,7 @@ def g_attn_trace():
     qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
     o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
     do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
-    buf = (ctypes.c_longlong * (3 * 2048))()
+    buf = (ctypes.c_longlong * (3 * 1024))()
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
     torch.cuda.synchronize()
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
@@ -412,18 +412,18 @@ def g_attn_trace():
     L.b200vq_trace_read(buf)
     ev = []
     for r in range(3):
-        for i in range(1024):
-            e, t = buf[r * 2048 + 2 * i], buf[r * 2048 + 2 * i + 1]
+        for i in range(512):
+            e, t = buf[r * 1024 + 2 * i], buf[r * 1024 + 2 * i + 1]
             if t:
                 ev.append((t, r, e))
     ev.sort()
     t0 = ev[0][0]
-    names = {100: "wait kk_full+sfree", 101: "got them", 102: "issued S/dP", 103: "wait km_full+p_full", 104: "got them", 105: "got km_full",
-             106: "issued dQ", 200: "wait s_full", 220: "got s_full", 240: "ld done", 260: "compute done", 280: "arrived p_full"}
+    names = {100: "wait loads", 107: "got loads, wait sfree", 101: "got sfree", 102: "issued S/dP", 103: "wait loads", 105: "got loads, wait p_full", 104: "got p_full", 199: "at softmax_bar",
+             106: "issued dV/dK", 200: "wait s_full", 220: "got s_full", 240: "ld done", 260: "compute done", 280: "arrived p_full"}
     role = {0: "mmaA ", 1: "mmaB ", 2: "sm2  "}
     start = next(i for i, (t, r, e) in enumerate(ev) if e == 100 and i > len(ev) // 2)
     prev = ev[start][0]
-    for t, r, e in ev[start:start + 48]:
+    for t, r, e in ev[start:start + 56]:
         print(f"{t - t0:9d} (+{t - prev:5d})  {role[r]}{names.get(e, e)}")
         prev = t
 
