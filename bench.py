@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="base", choices=["small", "base", "base_rq4", "large"])
+    ap.add_argument("--config", default="base", choices=["tiny", "small", "base", "base_rq4", "large"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
     ap.add_argument("--cta-group", type=int, default=int(os.environ.get("B200VQ_CTA_GROUP", "2")))
     ap.add_argument("--ref-batch", type=int, default=4, help="images per CPU step for --impl reference / cpu_baseline")
