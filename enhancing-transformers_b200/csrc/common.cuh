@@ -73,6 +73,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// tanh(x) = 1 - 2 / (exp(2x) + 1) with one ex2.approx and one rcp.approx (absolute error ~1e-7, far below the
+// tf32 rounding applied to the result).  libdevice's tanhf costs ~40 instructions and made the MLP-1 GEMM
+// epilogue-bound (1500 us vs 890 us for the same GEMM without the activation).
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));   // exp(2x) = 2^(2x log2 e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);                                                    // e = inf -> r = 0 -> 1; e = 0 -> -1
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

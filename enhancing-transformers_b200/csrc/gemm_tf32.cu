@@ -13,8 +13,9 @@
 //   b_major = 1 : B is [K_total, N]  row-major                 (dgrad reads W, wgrad reads X)
 // Split-K: split z contracts rows/cols [z*K, (z+1)*K) and writes C + z*c_split_stride.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  CG = 2 pairs two CTAs on one
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take alternate
+// 32-column chunks so that one warp's TMEM-load / TMA latencies hide behind the other's math).  CG = 2 pairs two CTAs on one
 // 256 x BN tile (tcgen05 cta_group::2): each CTA stages its 128 rows of A and half of B.
 #include "common.cuh"
 
@@ -42,7 +43,7 @@ struct GemmParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;        // 32 fp32 = one 128-byte swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 template <int BN, int CG>
 struct GemmCfg {
@@ -50,7 +51,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 4;
   static constexpr int B_BYTES = BN_CTA * kBK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 16384;     // per epilogue warp: out[2][4 KB] + in[2][4 KB]
+  static constexpr int STAGING_BYTES = 8 * 8192;      // per epilogue warp: out[4 KB] + in[4 KB]
   static constexpr int MAX_SMEM = 232448;             // 227 KB opt-in limit
   static constexpr int RING_BUDGET = MAX_SMEM - STAGING_BYTES - 1024 - 512;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
@@ -73,7 +74,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint64_t* in_full_all = bars + 2 * STAGES + 4;  // [4 warps][2]
+  uint64_t* in_full_all = bars + 2 * STAGES + 4;  // [8 epilogue warps]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
   const int warp = threadIdx.x >> 5;
@@ -93,7 +94,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the pair
+      mbar_init(&tmem_empty[a], 8 * CG);  // one arrive per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
@@ -188,17 +189,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps
-    // Each warp owns 32 rows of the tile (TMEM lane quarter q).  Per 32-column chunk: tcgen05.ld ->
-    // registers -> fused math -> 128B-swizzled smem box -> TMA store (fully coalesced, clipped at the
-    // matrix edge).  Residual / tanh' inputs arrive the same way through TMA loads, one chunk ahead.
+    // Each warp owns 32 rows of the tile (TMEM lane quarter q) and every other 32-column chunk.
+    // Per chunk: tcgen05.ld -> registers -> fused math -> 128B-swizzled smem box -> TMA store (fully
+    // coalesced, clipped at the matrix edge).  Residual / tanh' inputs arrive the same way through
+    // TMA loads issued one chunk ahead.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int ew = warp - 2;
-    uint8_t* out_buf = staging + ew * 16384;
-    uint8_t* in_buf = out_buf + 8192;
-    uint64_t* in_full = in_full_all + ew * 2;
+    const int ehalf = ew >> 2;
+    uint8_t* out_buf = staging + ew * 8192;
+    uint8_t* in_buf = out_buf + 4096;
+    uint64_t* in_full = in_full_all + ew;
     const uint32_t swz = lane & 7;
     const bool tma_in = p.in_mode != 0;
-    uint32_t in_issue = 0, in_use = 0, out_cnt = 0;
+    uint32_t in_cnt = 0;
     constexpr int NCHUNK = BN / 32;
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
@@ -210,35 +213,37 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = nb * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (tma_in && lane == 0) {   // first input chunk of this tile (its buffer was released by the previous tile)
-        mbar_arrive_expect_tx(&in_full[in_issue & 1], 4096);
-        tma_load_2d(in_buf + (in_issue & 1) * 4096, &tmIn, &in_full[in_issue & 1], n0, row0);
+      if (tma_in && ehalf < NCHUNK && lane == 0) {   // this warp's first input chunk of the tile (buffer free since the last tile)
+        mbar_arrive_expect_tx(in_full, 4096);
+        tma_load_2d(in_buf, &tmIn, in_full, n0 + ehalf * 32, row0);
       }
-      if (tma_in) ++in_issue;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const float* rrow = nullptr;
       if (p.res && row < p.M) rrow = p.res + (long long)(p.res_row_mod > 0 ? row % p.res_row_mod : row) * p.ldres;
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = ehalf; c < NCHUNK; c += 2) {
         const int col0 = n0 + c * 32;
-        if (tma_in && c + 1 < NCHUNK) {
-          __syncwarp();            // every lane has finished reading the buffer about to be refilled
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&in_full[in_issue & 1], 4096);
-            tma_load_2d(in_buf + (in_issue & 1) * 4096, &tmIn, &in_full[in_issue & 1], col0 + 32, row0);
-          }
-          ++in_issue;
-        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE + c * 32, v);
+        float4 a[8];
+        if (tma_in) {
+          mbar_wait(in_full, in_cnt & 1);
+          ++in_cnt;
+          const uint8_t* inb = in_buf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const float4*>(inb + ((j ^ swz) << 4));
+          __syncwarp();            // every lane holds its inputs: the buffer can be refilled
+          if (lane == 0 && c + 2 < NCHUNK) {
+            mbar_arrive_expect_tx(in_full, 4096);
+            tma_load_2d(in_buf, &tmIn, in_full, col0 + 64, row0);
+          }
+        }
         tmem_ld_wait();
-        const uint8_t* inb = in_buf + (in_use & 1) * 4096 + lane * 128;
-        if (tma_in) { mbar_wait(&in_full[in_use & 1], (in_use >> 1) & 1); ++in_use; }
-        // the staging buffer we are about to overwrite must have been read by its TMA store
-        if (lane == 0) bulk_wait_group_read<1>();
+        // the staging buffer must have been read by the TMA store of this warp's previous chunk
+        if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
-        uint8_t* outb = out_buf + (out_cnt & 1) * 4096 + lane * 128;
+        uint8_t* outb = out_buf + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -248,18 +253,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+          if (p.act == 1) { o.x = fast_tanh(o.x); o.y = fast_tanh(o.y); o.z = fast_tanh(o.z); o.w = fast_tanh(o.w); }
           if (tma_in) {
-            const float4 a = *reinterpret_cast<const float4*>(inb + ((j ^ swz) << 4));
             if (p.in_mode == 2) {
-              o.x *= 1.f - a.x * a.x; o.y *= 1.f - a.y * a.y; o.z *= 1.f - a.z * a.z; o.w *= 1.f - a.w * a.w;
+              o.x *= 1.f - a[j].x * a[j].x; o.y *= 1.f - a[j].y * a[j].y; o.z *= 1.f - a[j].z * a[j].z; o.w *= 1.f - a[j].w * a[j].w;
             } else {
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              o.x += a[j].x; o.y += a[j].y; o.z += a[j].z; o.w += a[j].w;
             }
           }
           if (rrow && col < p.N) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(rrow + col));
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + col));
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
           }
           if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
           *reinterpret_cast<float4*>(outb + ((j ^ swz) << 4)) = o;
@@ -267,10 +271,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (col0 < p.N && row0 < p.M) tma_store_3d(&tmC, out_buf + (out_cnt & 1) * 4096, col0, row0, z);
+          if (col0 < p.N && row0 < p.M) tma_store_3d(&tmC, out_buf, col0, row0, z);
           bulk_commit_group();
         }
-        ++out_cnt;
       }
       tcgen05_fence_before();
       __syncwarp();
