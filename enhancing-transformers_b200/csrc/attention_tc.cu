@@ -470,11 +470,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
         const uint32_t ph = (sd_it >> 1) & 1;
-        TRACE(0, 100);
         mbar_wait(&qk_full[s], ph);
-        TRACE(0, 107);
         mbar_wait(&sfree[s], ph ^ 1);
-        TRACE(0, 101);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qd = desc_advance(qd0, s * 4 * T64);
@@ -494,7 +491,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(kv_empty);
         }
         __syncwarp();
-        TRACE(0, 102);
       }
     }
   } else if (warp == kIssuerB) {
@@ -506,12 +502,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++dv_it) {
         const int s = dv_it & 1;
         const uint32_t ph = (dv_it >> 1) & 1;
-        TRACE(1, 103);
         mbar_wait(&qm_full[s], ph);
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        TRACE(1, 105);
         mbar_wait(&p_full[s], ph);
-        TRACE(1, 104);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
@@ -528,7 +521,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
         __syncwarp();
-        TRACE(1, 106);
       }
     }
   } else {
@@ -546,24 +538,25 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // lse / delta of a sub-tile are fetched one sub-tile ahead into registers.  The raw loaded
-      // values are only *used* (scaled, stored to smem) at the top of the next iteration: a warp
-      // stalls at the first use of a pending load, so using them here would put the global-load
-      // latency in front of the barrier every sub-tile.
-      float nl = 0.f, ne = 0.f;
-      bool nvalid = et < 64 && et < p.N;
-      if (nvalid) { nl = lb[et]; ne = eb[et]; }
+      // Per-column lse / delta: lane l of a warp keeps the values of query column (half*32 + l) of the
+      // current sub-tile in registers (fetched from global one sub-tile ahead; the raw values are only
+      // *used* at the top of the next iteration so the load latency is off the critical path) and the
+      // 32 columns are broadcast with warp shuffles.  Shared-memory / L1 reads are not an option here:
+      // while the N=64 tf32 MMAs run they take the SM's whole SRAM bandwidth and such reads cost
+      // ~1000 extra cycles per sub-tile (measured).
+      const int qcol = half * 32 + lane;
+      float raw_l = 0.f, raw_e = 0.f;
+      bool nvalid = qcol < p.N;
+      if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it & 1;
-        if (et < 64) {
-          Ls[s * 64 + et] = nvalid ? nl * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
-          Es[s * 64 + et] = nvalid ? ne : 0.f;
-          const int qi = (i + 1) * 64 + et;
+        const float myL = nvalid ? raw_l * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
+        const float myE = nvalid ? raw_e : 0.f;
+        {
+          const int qi = (i + 1) * 64 + qcol;
           nvalid = i + 1 < NS && qi < p.N;
-          if (nvalid) { nl = lb[qi]; ne = eb[qi]; }
+          if (nvalid) { raw_l = lb[qi]; raw_e = eb[qi]; }
         }
-        if (warp == 2) TRACE(2, 199);
-        softmax_bar();
         if (warp == 2) TRACE(2, 200);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         if (warp == 2) TRACE(2, 220);
@@ -574,31 +567,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
         if (warp == 2) TRACE(2, 240);
-        // per-column lse / delta: read through the L1 (warp-uniform 16-byte loads) when the tile is
-        // full -- shared-memory reads here compete with the tcgen05 operand fetch of the S^T / dP^T
-        // MMAs running at the same time (measured 1700 vs ~450 cycles for this loop)
-        const bool direct = (p.N & 63) == 0;
-        const float* lq = lb + i * 64 + half * 32;
-        const float* eq = eb + i * 64 + half * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 L, E;
-          if (direct) {
-            L = __ldg(reinterpret_cast<const float4*>(lq + j));
-            E = __ldg(reinterpret_cast<const float4*>(eq + j));
-            L.x *= kLog2eF; L.y *= kLog2eF; L.z *= kLog2eF; L.w *= kLog2eF;
-          } else {
-            L = *reinterpret_cast<const float4*>(&Ls[col + j]);
-            E = *reinterpret_cast<const float4*>(&Es[col + j]);
-          }
-          const float Lv[4] = {L.x, L.y, L.z, L.w}, Ev[4] = {E.x, E.y, E.z, E.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float pr = ex2_approx(fmaf(__uint_as_float(v[j + u]), c, -Lv[u]));
-            const float ds = pr * (__uint_as_float(g[j + u]) - Ev[u]);
-            v[j + u] = __float_as_uint(round_tf32(pr));
-            g[j + u] = __float_as_uint(round_tf32(ds));
-          }
+        for (int j = 0; j < 32; ++j) {
+          const float Lj = __shfl_sync(0xffffffffu, myL, j);
+          const float Ej = __shfl_sync(0xffffffffu, myE, j);
+          const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Lj));
+          const float ds = pr * (__uint_as_float(g[j]) - Ej);
+          v[j] = __float_as_uint(round_tf32(pr));
+          g[j] = __float_as_uint(round_tf32(ds));
         }
         if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + col, v);

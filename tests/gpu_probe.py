@@ -407,8 +407,6 @@ def g_attn_trace():
     buf = (ctypes.c_longlong * (3 * 1024))()
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
     torch.cuda.synchronize()
-    ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
-    torch.cuda.synchronize()
     L.b200vq_trace_read(buf)
     ev = []
     for r in range(3):
@@ -418,10 +416,10 @@ def g_attn_trace():
                 ev.append((t, r, e))
     ev.sort()
     t0 = ev[0][0]
-    names = {100: "wait loads", 107: "got loads, wait sfree", 101: "got sfree", 102: "issued S/dP", 103: "wait loads", 105: "got loads, wait p_full", 104: "got p_full", 199: "at softmax_bar",
-             106: "issued dV/dK", 200: "wait s_full", 220: "got s_full", 240: "ld done", 260: "compute done", 280: "arrived p_full"}
+    names = {100: "wait k_full", 107: "got k, wait sfree", 101: "got sfree", 102: "issued S", 103: "wait v/o_empty", 105: "got them, wait p_full", 104: "got p_full", 250: "max exchanged", 290: "pv accumulated",
+             106: "issued PV", 200: "wait s_full", 220: "got s_full", 240: "ld+max done", 260: "compute done", 280: "arrived p_full"}
     role = {0: "mmaA ", 1: "mmaB ", 2: "sm2  "}
-    start = next(i for i, (t, r, e) in enumerate(ev) if e == 100 and i > len(ev) // 2)
+    start = next(i for i, (t, r, e) in enumerate(ev) if e in (100, 200) and i > len(ev) // 2)
     prev = ev[start][0]
     for t, r, e in ev[start:start + 56]:
         print(f"{t - t0:9d} (+{t - prev:5d})  {role[r]}{names.get(e, e)}")
