@@ -88,7 +88,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   uint64_t* o_empty = bars + 16;  // [2]
   uint64_t* sfree = bars + 18;    // [2] S/P buffer consumed by the P.V MMAs (issuer B -> issuer A)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* xch = reinterpret_cast<float*>(bars + 22);   // [128][DH + 2] (m, l, o[DH]) of softmax group 1 for the end-of-item merge
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -99,8 +99,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
       mbar_init(&sfree[s], 1);
     }
     fence_barrier_init();
@@ -201,123 +201,101 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
-    // Two groups of four warps; group g owns the key tiles j = g (mod 2), i.e. S/P buffer g and P.V
-    // buffer g, with thread = query row (all 128 scores of the row).  Each group runs its own online
-    // softmax (m, l, o) over its half of the key tiles -- no per-tile exchange between threads -- and
-    // the two partial results are merged once per item (split-KV combine).  On every SM sub-partition
-    // one warp of each group is resident, half a period apart: while one is in its exp2 phase (XU
-    // pipe, 16 lanes/clk/SM: 1024 cycles per tile) the other does its max / P.V-accumulate phases.
+    // A query row is shared by two threads (warps w and w+4 address the same TMEM lanes): each
+    // takes 64 of the 128 scores of a tile and half of the head dim of the output; the row max
+    // (per tile) and the row sum (once per item) are exchanged through shared memory.
     const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const float c = p.scale * kLog2eF;
-    float* mine = xch + row_in_tile * (DH + 2);
-    uint32_t item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+    uint32_t t_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
-      float o[DH];
+      float o[OC];
 #pragma unroll
-      for (int i = 0; i < DH; ++i) o[i] = 0.f;
+      for (int i = 0; i < OC; ++i) o[i] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-      // global tile counter of this item's first tile; tile j of the item is tile number base + j
-      const uint32_t base = item_it * (uint32_t)T;
       auto accumulate_pv = [&](uint32_t it, float alpha) {
         const int sp = it & 1;
         mbar_wait(&o_full[sp], (it >> 1) & 1);
         tcgen05_fence_after();
+        uint32_t v[OC];
+        tmem_ld_cols<OC>(tmem_base + lane_off + 256 + sp * 64 + half * OC, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int cc = 0; cc < DH / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_off + 256 + sp * 64 + cc * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[cc * 32 + i] = fmaf(o[cc * 32 + i], alpha, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[sp]);
       };
-      bool have_prev = false;
-      uint32_t prev_it = 0;
-      for (int j = 0; j < T; ++j) {
-        const uint32_t t_it = base + j;
-        if ((int)(t_it & 1) != grp) continue;      // the other group's tile (buffer parity == group)
+      for (int j = 0; j < T; ++j, ++t_it) {
         const int s = t_it & 1;
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t sa = tmem_base + lane_off + s * 128;
-        const int kv_left = p.N - j * 128;          // columns >= kv_left of this tile are padding
+        const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
+        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
+        // one pass over TMEM: the thread's 64 scores stay in registers between max and exp
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(sa, v0);
+        tmem_ld_32x32(sa + 32, v1);
+        tmem_ld_wait();
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(sa + cc * 32, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (cc * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_left) v0[i] = 0xff800000u;          // -inf: padded key columns
+          if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
         }
+        float* xs = xch + (t_it & 1) * 256;
+        xs[half * 128 + row_in_tile] = mx;
+        softmax_bar();
+        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
-        float sum = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(sa + cc * 32, v);
-          tmem_ld_wait();
+        float sum = 0.f, sum1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (cc * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY;
-            const float e = ex2_approx(fmaf(x, c, -mc));
-            sum += e;
-            v[i] = __float_as_uint(round_tf32(e));
-          }
-          tmem_st_32x32(sa + cc * 32, v);
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
+          sum += e0; sum1 += e1;
+          v0[i] = __float_as_uint(round_tf32(e0));
+          v1[i] = __float_as_uint(round_tf32(e1));
         }
+        sum += sum1;
+        tmem_st_32x32(sa, v0);
+        tmem_st_32x32(sa + 32, v1);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
         l = fmaf(l, alpha, sum);
-        if (have_prev) accumulate_pv(prev_it, alpha_prev);
-        have_prev = true;
-        prev_it = t_it;
+        if (j >= 1) accumulate_pv(t_it - 1, alpha_prev);
         alpha_prev = alpha;
         m = m_new;
       }
-      if (have_prev) accumulate_pv(prev_it, alpha_prev);
-      // ---- merge the two groups' partial softmax states and store
-      const uint32_t first_parity = base & 1;        // group that owns tile 0 of this item always has >= 1 tile
-      const int writer = (int)first_parity;          // ... and does the final store
-      if (grp != writer) {
-        mine[0] = m; mine[1] = l;
-#pragma unroll
-        for (int i = 0; i < DH; ++i) mine[2 + i] = o[i];
-      }
+      accumulate_pv(t_it - 1, alpha_prev);
+      float* ls = xch + 512;
+      ls[half * 128 + row_in_tile] = l;
       softmax_bar();
-      if (grp == writer) {
-        const float m2 = mine[0], l2 = mine[1];
-        const float mm = fmaxf(m, m2);
-        const float a1 = ex2_approx((m - mm) * c), a2 = ex2_approx((m2 - mm) * c);   // ex2(-inf) = 0 for an empty group
-        l = l * a1 + l2 * a2;
-        const int row = qt * 128 + row_in_tile;
-        if (row < p.N) {
-          const float inv = 1.f / l;
-          float* op = p.out + ((long long)b * p.N + row) * inner + h * DH;
+      l += ls[(half ^ 1) * 128 + row_in_tile];
+      const int row = qt * 128 + row_in_tile;
+      if (row < p.N) {
+        const float inv = 1.f / l;
+        float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
 #pragma unroll
-          for (int i = 0; i < DH; i += 4) {
-            float4 r = make_float4((o[i] * a1 + mine[2 + i] * a2) * inv, (o[i + 1] * a1 + mine[3 + i] * a2) * inv,
-                                   (o[i + 2] * a1 + mine[4 + i] * a2) * inv, (o[i + 3] * a1 + mine[5 + i] * a2) * inv);
-            if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-            *reinterpret_cast<float4*>(op + i) = r;
-          }
-          p.lse[((long long)b * p.heads + h) * p.N + row] = mm * p.scale + logf(l);
+        for (int i = 0; i < OC; i += 4) {
+          float4 r = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+          if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+          *reinterpret_cast<float4*>(op + i) = r;
         }
+        if (half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
       }
-      softmax_bar();   // the exchange area is rewritten by the next item only after it has been read
+      softmax_bar();   // ls is rewritten by the next item only after everyone has read it
     }
   }
   tcgen05_fence_before();
@@ -353,7 +331,7 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 512 + 128 * (DH + 2) * 4;
+  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 512 + 3 * 256 * 4;
   auto kern = attn_fwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
