@@ -368,7 +368,10 @@ def g_precision():
     from oracle import vitvq_oracle as O
     import enhancing_transformers_b200 as etb
     torch.backends.cuda.matmul.allow_tf32 = False
-    for name, B in (("small", 4), ("base", 4)):
+    import sys
+    which = [a for a in sys.argv[3:]] or ["small", "base"]
+    for name in which:
+        B = 2 if name == "large" else 4
         cfg = O.CONFIGS[name]
         sd = O.init_vitvq_sd(cfg, seed=0)
         img = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(0))
@@ -382,7 +385,9 @@ def g_precision():
             enc, dec, vq, pre, post = mods
             h = enc(img.cuda()); z = pre(h)
             zq, _, idx = vq(z)
-            zq64, _, idx64 = O.vq_forward(z64.float(), sd["quantizer.embedding.weight"].cuda())
+            qc = cfg["quantizer"]
+            zq64, _, idx64 = O.vq_forward(z64.float(), sd["quantizer.embedding.weight"].cuda(), qc.get("beta", 0.25),
+                                          qc.get("use_residual", False), qc.get("num_quantizers"))
             rec = dec(post(zq))
             t64 = zq.double() @ sd64["post_quant.weight"].t() + sd64["post_quant.bias"]
             rec64 = O.vit_decoder(sd64, t64, patch=p, depth=d["depth"], heads=d["heads"], grid_hw=(g, g), prefix="decoder.")
@@ -432,12 +437,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
         GROUPS[sys.argv[2]]()
         sys.exit(0)
-    names = sys.argv[1:] or list(GROUPS)
+    names = [a for a in sys.argv[1:] if a in GROUPS] or list(GROUPS)
+    extra = [a for a in sys.argv[1:] if a not in GROUPS]
     for n in names:
         t0 = time.time()
         print(f"===== {n}", flush=True)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n], timeout=300)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n] + extra, timeout=300)
             print(f"===== {n}: exit {r.returncode} in {time.time()-t0:.1f}s", flush=True)
         except subprocess.TimeoutExpired:
             print(f"===== {n}: TIMEOUT", flush=True)
