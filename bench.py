@@ -293,7 +293,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 1.572e9 if args.config == "base" and B == 128 else None,
+                         "traffic": 1.562e9 if args.config == "base" and B == 128 else None,
                          "traffic_note": "dram read+write bytes of one to_qkv launch (M=131072 N=2304 K=768) from profiles/ ncu --set full; "
                                          "algorithmic bytes of that launch: 1.618e9",
                          "peak_source": peaks["source"] + ": cuBLAS bf16 sustained; tf32 issues at half the bf16 rate, so frac <= ~0.5 by construction",

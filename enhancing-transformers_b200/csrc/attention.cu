@@ -13,23 +13,30 @@ int attention_forward_tc(const float*, float*, float*, int, int, int, int, float
 int attention_backward_tc(const float*, const float*, const float*, const float*, float*, int, int, int, int, float, int,
                           cudaStream_t);
 
-// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per (b, n, h), fully coalesced
-__global__ void attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ dout, float* __restrict__ delta,
-                                  int B, int N, int heads, int dh) {
-  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)B * N * heads;
-  if (gw >= total) return;
-  const int h = (int)(gw % heads);
-  const long long bn = gw / heads;
-  const float* po = o + bn * heads * dh + h * dh;
-  const float* pd = dout + bn * heads * dh + h * dh;
-  float s = 0.f;
-  for (int d = lane; d < dh; d += 32) s += po[d] * pd[d];
-  s = warp_sum(s);
-  if (lane == 0) {
-    const long long b = bn / N, n = bn % N;
-    delta[(b * heads + h) * N + n] = s;
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d].  HBM-bound: one float4 of O and dO per thread, dh/4 adjacent
+// lanes per (row, head) reduced with shuffles, so a warp streams 512 contiguous bytes of each tensor.
+template <int LANES>   // lanes per (row, head) = dh / 4: 16 (dh 64) or 8 (dh 32)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ dout, float* __restrict__ delta, long long groups,
+                  int N, int heads) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long total = groups * LANES;          // one thread per float4
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ((total + 31) / 32) * 32; i += stride) {
+    float s = 0.f;
+    if (i < total) {
+      const float4 a = reinterpret_cast<const float4*>(o)[i];
+      const float4 b = reinterpret_cast<const float4*>(dout)[i];
+      s = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (i < total && (i & (LANES - 1)) == 0) {
+      const long long g = i / LANES;                // (b*N + n) * heads + h
+      const int h = (int)(g % heads);
+      const long long bn = g / heads;
+      const long long b = bn / N, n = bn % N;
+      delta[(b * heads + h) * N + n] = s;
+    }
   }
 }
 
@@ -44,8 +51,13 @@ int attention_backward(const float* qkv, const float* out, const float* lse, con
                        int B, int N, int heads, int dh, float scale, int round_out, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
-  const long long warps = (long long)B * N * heads;
-  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(out, dout, delta, B, N, heads, dh);
+  const long long groups = (long long)B * N * heads;
+  const long long threads = groups * (dh / 4);
+  long long blocks = (threads + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dh == 64) attn_delta_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
+  else          attn_delta_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
   B200_LAUNCH_OK("attn_delta_kernel");
   return attention_backward_tc(qkv, dout, lse, delta, dqkv, B, N, heads, dh, scale, round_out, stream);
 }

@@ -53,6 +53,8 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]) 
   if constexpr (NC == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
 }
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barrier of the two softmax warps that share TMEM lane quarter q (ids 2..5, 64 threads)
+__device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory"); }
 constexpr float kLog2eF = 1.4426950408889634f;
 
 struct AttnTcParams {
@@ -243,16 +245,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         tmem_ld_32x32(sa, v0);
         tmem_ld_32x32(sa + 32, v1);
         tmem_ld_wait();
+        if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
+            if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          }
+        }
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= kv_left) v0[i] = 0xff800000u;          // -inf: padded key columns
-          if (32 + i >= kv_left) v1[i] = 0xff800000u;
-          mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
         float* xs = xch + (t_it & 1) * 256;
         xs[half * 128 + row_in_tile] = mx;
-        softmax_bar();
+        pair_bar(q);                                        // only the two warps that share these rows
         mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
@@ -281,7 +286,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       accumulate_pv(t_it - 1, alpha_prev);
       float* ls = xch + 512;
       ls[half * 128 + row_in_tile] = l;
-      softmax_bar();
+      pair_bar(q);
       l += ls[(half ^ 1) * 128 + row_in_tile];
       const int row = qt * 128 + row_in_tile;
       if (row < p.N) {
@@ -295,7 +300,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         }
         if (half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
       }
-      softmax_bar();   // ls is rewritten by the next item only after everyone has read it
+      pair_bar(q);     // ls is rewritten by the next item only after the partner has read it
     }
   }
   tcgen05_fence_before();
