@@ -268,8 +268,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
           const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
           sum += e0; sum1 += e1;
-          v0[i] = __float_as_uint(round_tf32(e0));
-          v1[i] = __float_as_uint(round_tf32(e1));
+          v0[i] = tf32_bits_for_mma(e0);
+          v1[i] = tf32_bits_for_mma(e1);
         }
         sum += sum1;
         tmem_st_32x32(sa, v0);
@@ -578,8 +578,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           const float Ej = __shfl_sync(0xffffffffu, myE, j);
           const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Lj));
           const float ds = pr * (__uint_as_float(g[j]) - Ej);
-          v[j] = __float_as_uint(round_tf32(pr));
-          g[j] = __float_as_uint(round_tf32(ds));
+          v[j] = tf32_bits_for_mma(pr);
+          g[j] = tf32_bits_for_mma(ds);
         }
         if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + col, v);
@@ -799,10 +799,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
+        if (kv_left >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
-          g[j] = __float_as_uint(round_tf32(pr * (__uint_as_float(g[j]) - dl)));
+          for (int j = 0; j < 32; ++j)
+            g[j] = tf32_bits_for_mma(ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) * (__uint_as_float(g[j]) - dl));
+        } else {                                    // ragged last tile: padded key columns contribute nothing
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = (j < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -lse2)) : 0.f;
+            g[j] = tf32_bits_for_mma(pr * (__uint_as_float(g[j]) - dl));
+          }
         }
         tmem_st_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_st_wait();

@@ -73,6 +73,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// Same rounding for a value that is consumed *only* as a tcgen05 kind::tf32 operand: the tensor core drops the
+// low 13 bits itself, so adding half an ulp is enough (one integer op).
+__device__ __forceinline__ uint32_t tf32_bits_for_mma(float x) { return __float_as_uint(x) + 0x1000u; }
 // tanh(x) = 1 - 2 / (exp(2x) + 1) with one ex2.approx and one rcp.approx (absolute error ~1e-7, far below the
 // tf32 rounding applied to the result).  libdevice's tanhf costs ~40 instructions and made the MLP-1 GEMM
 // epilogue-bound (1500 us vs 890 us for the same GEMM without the activation).
