@@ -69,133 +69,144 @@ def _flat2d(x: torch.Tensor) -> torch.Tensor:
 
 
 class PreNorm(nn.Module):
+    """LayerNorm in front of a sub-block; parameter container (`norm`, `fn`) + stand-alone forward."""
+
     def __init__(self, dim: int, fn: nn.Module) -> None:
         super().__init__()
-        self.norm = nn.LayerNorm(dim)
-        self.fn = fn
+        self.norm, self.fn = nn.LayerNorm(dim), fn
 
     def forward(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
-        y = Fn.LayerNormFn.apply(_flat2d(x), self.norm.weight, self.norm.bias, False).view_as(x)
-        return self.fn(y, **kwargs)
+        flat = _flat2d(x)
+        normed = Fn.LayerNormFn.apply(flat, self.norm.weight, self.norm.bias, False)
+        return self.fn(normed.view_as(x), **kwargs)
 
 
 class FeedForward(nn.Module):
+    """Linear -> Tanh -> Linear; `net.0` / `net.2` hold the weights (checkpoint keys)."""
+
     def __init__(self, dim: int, hidden_dim: int) -> None:
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.Tanh(), nn.Linear(hidden_dim, dim))
+        up, down = nn.Linear(dim, hidden_dim), nn.Linear(hidden_dim, dim)
+        self.net = nn.Sequential(up, nn.Tanh(), down)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = Fn.LinearFn.apply(_flat2d(x), self.net[0].weight, self.net[0].bias, 1, False)
-        y = Fn.LinearFn.apply(h, self.net[2].weight, self.net[2].bias, 0, False)
-        return y.view(*x.shape[:-1], y.shape[-1])
+        up, down = self.net[0], self.net[2]
+        hidden = Fn.LinearFn.apply(_flat2d(x), up.weight, up.bias, 1, False)      # bias + tanh fused in the GEMM epilogue
+        y = Fn.LinearFn.apply(hidden, down.weight, down.bias, 0, False)
+        return y.view(*x.shape[:-1], -1)
 
 
 class Attention(nn.Module):
+    """Multi-head self-attention; `to_qkv` (no bias) and `to_out` hold the weights."""
+
     def __init__(self, dim: int, heads: int = 8, dim_head: int = 64) -> None:
         super().__init__()
-        inner_dim = dim_head * heads
-        project_out = not (heads == 1 and dim_head == dim)
-        self.heads = heads
-        self.dim_head = dim_head
+        self.heads, self.dim_head = heads, dim_head
         self.scale = dim_head ** -0.5
-        self.attend = nn.Softmax(dim=-1)          # kept for module-tree parity; the kernel fuses it
-        self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
-        self.to_out = nn.Linear(inner_dim, dim) if project_out else nn.Identity()
+        width = heads * dim_head
+        self.attend = nn.Softmax(dim=-1)          # module-tree parity only; the kernel fuses the softmax
+        self.to_qkv = nn.Linear(dim, 3 * width, bias=False)
+        single_head_identity = heads == 1 and dim_head == dim
+        self.to_out = nn.Identity() if single_head_identity else nn.Linear(width, dim)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        B, N, _ = x.shape
+        batch, tokens, _ = x.shape
         qkv = Fn.LinearFn.apply(_flat2d(x), self.to_qkv.weight, None, 0, False)
-        o = Fn.AttentionCoreFn.apply(qkv, B, N, self.heads, self.dim_head)
+        ctx = Fn.AttentionCoreFn.apply(qkv, batch, tokens, self.heads, self.dim_head)
         if isinstance(self.to_out, nn.Linear):
-            o = Fn.LinearFn.apply(o, self.to_out.weight, self.to_out.bias, 0, False)
-        return o.view(B, N, -1)
+            ctx = Fn.LinearFn.apply(ctx, self.to_out.weight, self.to_out.bias, 0, False)
+        return ctx.view(batch, tokens, -1)
 
 
 class Transformer(nn.Module):
+    """`depth` pre-norm blocks + final LayerNorm; forward runs each block as one fused autograd unit."""
+
     def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int) -> None:
         super().__init__()
-        self.layers = nn.ModuleList([])
-        for _ in range(depth):
-            self.layers.append(nn.ModuleList([PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head)),
-                                              PreNorm(dim, FeedForward(dim, mlp_dim))]))
+        blocks = [nn.ModuleList([PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head)),
+                                 PreNorm(dim, FeedForward(dim, mlp_dim))]) for _ in range(depth)]
+        self.layers = nn.ModuleList(blocks)
         self.norm = nn.LayerNorm(dim)
         self.heads, self.dim_head = heads, dim_head
         self.round_final = False    # decoder sets it: its final LN only feeds the to_pixel GEMM
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        B, N, D = x.shape
+        batch, tokens, width = x.shape
         h = _flat2d(x)
-        for attn, ff in self.layers:
-            a, f = attn.fn, ff.fn
-            if not isinstance(a.to_out, nn.Linear):
+        for pre_attn, pre_ff in self.layers:
+            att, ff = pre_attn.fn, pre_ff.fn
+            if not isinstance(att.to_out, nn.Linear):
                 raise NotImplementedError("heads == 1 and dim_head == dim (no output projection) is not built")
-            h = Fn.TransformerLayerFn.apply(h, attn.norm.weight, attn.norm.bias, a.to_qkv.weight, a.to_out.weight,
-                                            a.to_out.bias, ff.norm.weight, ff.norm.bias, f.net[0].weight, f.net[0].bias,
-                                            f.net[2].weight, f.net[2].bias, B, N, a.heads, a.dim_head)
+            h = Fn.TransformerLayerFn.apply(
+                h, pre_attn.norm.weight, pre_attn.norm.bias, att.to_qkv.weight, att.to_out.weight, att.to_out.bias,
+                pre_ff.norm.weight, pre_ff.norm.bias, ff.net[0].weight, ff.net[0].bias, ff.net[2].weight, ff.net[2].bias,
+                batch, tokens, att.heads, att.dim_head)
         h = Fn.LayerNormFn.apply(h, self.norm.weight, self.norm.bias, self.round_final)
-        return h.view(B, N, D)
+        return h.view(batch, tokens, width)
+
+
+class _Geometry:
+    """image / patch bookkeeping shared by encoder and decoder (reference layers.py:157-166,189-198)"""
+
+    def __init__(self, image_size: Size2, patch_size: Size2, channels: int) -> None:
+        ih, iw = _pair(image_size)
+        ph, pw = _pair(patch_size)
+        assert ih % ph == 0 and iw % pw == 0, 'Image dimensions must be divisible by the patch size.'
+        if ph != pw or ph % 4:
+            raise NotImplementedError("b200vq: square patches with side % 4 == 0 only")
+        self.image_hw = (ih, iw)
+        self.patch = ph
+        self.grid = (ih // ph, iw // pw)
+        self.num_patches = self.grid[0] * self.grid[1]
+        self.patch_dim = channels * ph * pw
+
+    def pos_table(self, dim: int) -> nn.Parameter:
+        table = torch.from_numpy(sincos_table(dim, self.grid)).unsqueeze(0)
+        return nn.Parameter(table, requires_grad=False)      # frozen, but part of the state dict like the reference's
 
 
 class ViTEncoder(nn.Module):
-    """reference layers.py:153-182"""
+    """reference layers.py:153-182: patch-embed conv (k = s = patch) + positional table + transformer"""
 
     def __init__(self, image_size: Size2, patch_size: Size2, dim: int, depth: int, heads: int, mlp_dim: int,
                  channels: int = 3, dim_head: int = 64) -> None:
         super().__init__()
-        image_height, image_width = _pair(image_size)
-        patch_height, patch_width = _pair(patch_size)
-        assert image_height % patch_height == 0 and image_width % patch_width == 0, \
-            'Image dimensions must be divisible by the patch size.'
-        if patch_height != patch_width or patch_height % 4:
-            raise NotImplementedError("b200vq: square patches with side % 4 == 0 only")
-        grid = (image_height // patch_height, image_width // patch_width)
-        self.num_patches = grid[0] * grid[1]
-        self.patch_dim = channels * patch_height * patch_width
-        self.patch = patch_height
-        # nn.Sequential(conv, rearrange) in the reference; index 0 keeps the checkpoint key
-        self.to_patch_embedding = nn.Sequential(nn.Conv2d(channels, dim, kernel_size=patch_size, stride=patch_size),
-                                                nn.Identity())
-        self.en_pos_embedding = nn.Parameter(torch.from_numpy(sincos_table(dim, grid)).unsqueeze(0), requires_grad=False)
+        geo = _Geometry(image_size, patch_size, channels)
+        self.num_patches, self.patch_dim, self.patch = geo.num_patches, geo.patch_dim, geo.patch
+        conv = nn.Conv2d(channels, dim, kernel_size=patch_size, stride=patch_size)
+        self.to_patch_embedding = nn.Sequential(conv, nn.Identity())     # index 0 keeps the checkpoint key
+        self.en_pos_embedding = geo.pos_table(dim)
         self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim)
         _init_like_reference(self)
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         conv = self.to_patch_embedding[0]
-        B = img.shape[0]
-        x = Fn.PatchEmbedFn.apply(img.contiguous(), conv.weight, conv.bias, self.en_pos_embedding, self.patch)
-        return self.transformer(x.view(B, self.num_patches, -1))
+        tokens = Fn.PatchEmbedFn.apply(img.contiguous(), conv.weight, conv.bias, self.en_pos_embedding, self.patch)
+        return self.transformer(tokens.view(img.shape[0], self.num_patches, -1))
 
 
 class ViTDecoder(nn.Module):
-    """reference layers.py:185-217"""
+    """reference layers.py:185-217: positional table + transformer + conv-transpose (k = s = patch) to pixels"""
 
     def __init__(self, image_size: Size2, patch_size: Size2, dim: int, depth: int, heads: int, mlp_dim: int,
                  channels: int = 3, dim_head: int = 64) -> None:
         super().__init__()
-        image_height, image_width = _pair(image_size)
-        patch_height, patch_width = _pair(patch_size)
-        assert image_height % patch_height == 0 and image_width % patch_width == 0, \
-            'Image dimensions must be divisible by the patch size.'
-        if patch_height != patch_width or patch_height % 4:
-            raise NotImplementedError("b200vq: square patches with side % 4 == 0 only")
-        grid = (image_height // patch_height, image_width // patch_width)
-        self.num_patches = grid[0] * grid[1]
-        self.patch_dim = channels * patch_height * patch_width
-        self.patch = patch_height
-        self.image_hw = (image_height, image_width)
+        geo = _Geometry(image_size, patch_size, channels)
+        self.num_patches, self.patch_dim, self.patch, self.image_hw = geo.num_patches, geo.patch_dim, geo.patch, geo.image_hw
         self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim)
         self.transformer.round_final = True
-        self.de_pos_embedding = nn.Parameter(torch.from_numpy(sincos_table(dim, grid)).unsqueeze(0), requires_grad=False)
-        self.to_pixel = nn.Sequential(nn.Identity(),
-                                      nn.ConvTranspose2d(dim, channels, kernel_size=patch_size, stride=patch_size))
+        self.de_pos_embedding = geo.pos_table(dim)
+        deconv = nn.ConvTranspose2d(dim, channels, kernel_size=patch_size, stride=patch_size)
+        self.to_pixel = nn.Sequential(nn.Identity(), deconv)             # index 1 keeps the checkpoint key
         _init_like_reference(self)
 
     def forward(self, token: torch.Tensor) -> torch.Tensor:
-        B, N, D = token.shape
+        batch, tokens, width = token.shape
         x = Fn.AddPosFn.apply(_flat2d(token), self.de_pos_embedding)
-        x = self.transformer(x.view(B, N, D))
-        convt = self.to_pixel[1]
-        return Fn.ToPixelFn.apply(_flat2d(x), convt.weight, convt.bias, B, self.image_hw[0], self.image_hw[1], self.patch)
+        x = self.transformer(x.view(batch, tokens, width))
+        deconv = self.to_pixel[1]
+        height, width_px = self.image_hw
+        return Fn.ToPixelFn.apply(_flat2d(x), deconv.weight, deconv.bias, batch, height, width_px, self.patch)
 
     def get_last_layer(self) -> nn.Parameter:
         return self.to_pixel[-1].weight
