@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 python tests/gpu_probe.py attention 2>&1 | tail -4
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
+timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 60 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "(attention and (16 or 24 or 130)) or (gemm_nt and 64) or vq_matches or gemm_epilogues" > gpurun_out/sanitizer_racecheck_full.txt 2>&1
+grep -E "Race reported|Error:|Warning:|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_racecheck_full.txt | sed 's/=========//' | cut -c1-260 | sort | uniq -c | sort -rn | head -30
