@@ -10,7 +10,6 @@ parameters, in a cached shadow copy that is refreshed when the parameter's versi
 changes."""
 from __future__ import annotations
 
-from typing import Dict, Tuple
 
 import torch
 
@@ -22,27 +21,31 @@ Tensor = torch.Tensor
 # that tests and bench.py can pin it
 GEMM_CTA_GROUP = 2
 
-_shadow: Dict[Tuple[int, int], Tuple[int, Tensor]] = {}
+_SHADOW_ATTR = "_b200vq_tf32_shadow"
 
 
 def tf32_shadow(w: Tensor) -> Tensor:
-    """tf32-rounded copy of a parameter, cached per (storage address, numel) and refreshed when
-    the parameter's version counter moves (optimizer steps bump it)."""
-    key = (w.data_ptr(), w.numel())
-    ent = _shadow.get(key)
+    """tf32-rounded copy of a parameter.  The copy hangs off the parameter object itself (so it lives and
+    dies with it -- a global cache keyed by address would hand a new parameter allocated at a recycled
+    address the previous owner's values) and is refreshed when the parameter's version counter moves
+    (in-place optimizer steps, ``load_state_dict`` and ``copy_`` all bump it)."""
+    ent = getattr(w, _SHADOW_ATTR, None)
     ver = w._version
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == ver and ent[1].device == w.device:
         return ent[1]
     src = w.detach()
     if not src.is_contiguous():
         src = src.contiguous()
-    out = ops.round_tf32(src, ent[1] if ent is not None and ent[1].shape == src.shape else None)
-    _shadow[key] = (ver, out)
+    out = ops.round_tf32(src, ent[1] if ent is not None and ent[1].shape == src.shape and ent[1].device == src.device else None)
+    try:
+        setattr(w, _SHADOW_ATTR, (ver, out))
+    except AttributeError:      # exotic tensor subclasses without a __dict__: just do not cache
+        pass
     return out
 
 
 def clear_shadow_cache() -> None:
-    _shadow.clear()
+    """kept for API compatibility: shadows are per-parameter attributes now, nothing global to clear"""
 
 
 def _wgrad(dy: Tensor, x: Tensor, rows: int, cols: int) -> Tensor:
@@ -71,21 +74,20 @@ class TransformerLayerFn(torch.autograd.Function):
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, ln2_w, ln2_b, True)
         t = ops.gemm(h2, w1r, M, mlp, D, bias=b1, act=1, round_out=True, cta_group=cg)
         x2 = ops.gemm(t, w2r, M, D, mlp, bias=b2, res=x1, cta_group=cg)
-        ctx.save_for_backward(x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, w_qkv, w_out, ln2_w, w1, w2)
+        ctx.save_for_backward(x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, ln2_w, wq, wo, w1r, w2r)
         ctx.dims = (B, N, heads, dh)
         return x2
 
     @staticmethod
     def backward(ctx, g):
         cg = GEMM_CTA_GROUP
-        x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, w_qkv, w_out, ln2_w, w1, w2 = ctx.saved_tensors
+        x, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, t, ln1_w, ln2_w, wq, wo, w1r, w2r = ctx.saved_tensors
         B, N, heads, dh = ctx.dims
         M, D = x.shape
         inner = heads * dh
-        mlp = w1.shape[0]
+        mlp = w1r.shape[0]
         scale = dh ** -0.5
         g = g.contiguous()
-        wq, wo, w1r, w2r = tf32_shadow(w_qkv), tf32_shadow(w_out), tf32_shadow(w1), tf32_shadow(w2)
         # ---- feed-forward branch
         db2 = ops.colsum(g)
         dw2 = _wgrad(g, t, D, mlp)
@@ -134,23 +136,24 @@ class LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[0]
         xr = ops.round_tf32(x)
-        y = ops.gemm(xr, tf32_shadow(w), M, N, K, bias=b, act=int(act), round_out=bool(round_out), cta_group=GEMM_CTA_GROUP)
-        ctx.save_for_backward(xr, w, y if act else None)
+        wr = tf32_shadow(w)
+        y = ops.gemm(xr, wr, M, N, K, bias=b, act=int(act), round_out=bool(round_out), cta_group=GEMM_CTA_GROUP)
+        ctx.save_for_backward(xr, wr, y if act else None)
         ctx.has_bias = b is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
-        xr, w, y = ctx.saved_tensors
+        xr, wr, y = ctx.saved_tensors
         M, K = xr.shape
-        N = w.shape[0]
+        N = wr.shape[0]
         g = g.contiguous()
         if y is not None:   # tanh backward folded into an elementwise pass of the dgrad epilogue is
             g = g * (1 - y * y)   # only available fused (TransformerLayerFn); stand-alone path keeps it simple
         gr = ops.round_tf32(g)
         db = ops.colsum(gr) if ctx.has_bias else None
         dw = _wgrad(gr, xr, N, K)
-        dx = ops.gemm(gr, tf32_shadow(w), M, K, N, b_major=1, cta_group=GEMM_CTA_GROUP)
+        dx = ops.gemm(gr, wr, M, K, N, b_major=1, cta_group=GEMM_CTA_GROUP)
         return dx, dw, db, None, None
 
 
@@ -185,9 +188,10 @@ class PatchEmbedFn(torch.autograd.Function):
         n_tok = (H // p) * (W // p)
         patches = ops.patchify(img, p, True)
         M, pd = patches.shape
-        x = ops.gemm(patches, tf32_shadow(w).view(D, pd), M, D, pd, bias=b, res=pos.view(n_tok, D), res_row_mod=n_tok,
+        wr = tf32_shadow(w)
+        x = ops.gemm(patches, wr.view(D, pd), M, D, pd, bias=b, res=pos.view(n_tok, D), res_row_mod=n_tok,
                      cta_group=GEMM_CTA_GROUP)
-        ctx.save_for_backward(patches, w)
+        ctx.save_for_backward(patches, wr)
         ctx.geom = (B, C, H, W, p)
         return x
 
@@ -202,7 +206,7 @@ class PatchEmbedFn(torch.autograd.Function):
         dw = _wgrad(g, patches, D, pd).view_as(w)
         dimg = None
         if ctx.needs_input_grad[0]:
-            dpat = ops.gemm(g, tf32_shadow(w).view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
+            dpat = ops.gemm(g, w.view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
             dimg = ops.unpatchify(dpat, None, B, C, H, W, p)
         return dimg, dw, db, None, None
 
@@ -216,9 +220,10 @@ class ToPixelFn(torch.autograd.Function):
         M, D = x.shape
         C = w.shape[1]
         pd = C * p * p
-        y = ops.gemm(x, tf32_shadow(w).view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
+        wr = tf32_shadow(w)
+        y = ops.gemm(x, wr.view(D, pd), M, pd, D, b_major=1, cta_group=GEMM_CTA_GROUP)
         img = ops.unpatchify(y, b, B, C, H, W, p)
-        ctx.save_for_backward(x, w)
+        ctx.save_for_backward(x, wr)
         ctx.geom = (B, C, H, W, p)
         return img
 
@@ -231,7 +236,7 @@ class ToPixelFn(torch.autograd.Function):
         dy = ops.patchify(g.contiguous(), p, True)
         db = ops.colsum(dy).view(C, p * p).sum(dim=1)
         dw = _wgrad(x, dy, D, pd).view_as(w)
-        dx = ops.gemm(dy, tf32_shadow(w).view(D, pd), M, D, pd, cta_group=GEMM_CTA_GROUP)
+        dx = ops.gemm(dy, w.view(D, pd), M, D, pd, cta_group=GEMM_CTA_GROUP)
         return dx, dw, db, None, None, None, None
 
 

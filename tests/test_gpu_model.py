@@ -136,3 +136,29 @@ def test_sub_modules_run_standalone():
     assert relmax(y.detach().cpu(), yr.detach()) < 2e-3
     y.sum().backward(); yr.sum().backward()
     assert relmax(x.grad.cpu(), xr.grad) < 5e-3
+
+
+def test_tf32_shadow_follows_parameter_identity_and_version():
+    """the rounded weight copy must track in-place updates and must not leak between parameters that happen to be
+    allocated at the same device address"""
+    torch.manual_seed(0)
+    x = torch.randn(64, 64, device="cuda")
+    outs = []
+    for seed in (1, 2, 3):                       # fresh modules of identical shape: the allocator recycles addresses
+        torch.manual_seed(seed)
+        ff = etb.FeedForward(64, 96).cuda()
+        y = ff(x)
+        sd = {k: v.detach().cpu() for k, v in ff.state_dict().items()}
+        ref = O.feed_forward(x.cpu(), sd["net.0.weight"], sd["net.0.bias"], sd["net.2.weight"], sd["net.2.bias"])
+        assert relmax(y.detach().cpu(), ref) < 2e-3
+        outs.append(y.detach().clone())
+        del ff, y
+    assert not torch.allclose(outs[0], outs[1])
+    ff = etb.FeedForward(64, 96).cuda()
+    y0 = ff(x).detach().clone()
+    with torch.no_grad():
+        ff.net[0].weight.mul_(0.5)               # what an optimizer step does: bumps the version counter
+    y1 = ff(x).detach()
+    sd = {k: v.detach().cpu() for k, v in ff.state_dict().items()}
+    ref = O.feed_forward(x.cpu(), sd["net.0.weight"], sd["net.0.bias"], sd["net.2.weight"], sd["net.2.bias"])
+    assert relmax(y1.cpu(), ref) < 2e-3 and not torch.allclose(y0, y1)
