@@ -52,7 +52,6 @@ template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]) {
   if constexpr (NC == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // named barrier of the two softmax warps that share TMEM lane quarter q (ids 2..5, 64 threads)
 __device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory"); }
 constexpr float kLog2eF = 1.4426950408889634f;
@@ -385,9 +384,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint8_t* Ks = smem;
   uint8_t* Vs = smem + T128;
   uint8_t* St = smem + 2 * T128;        // stage s at St + s*4*T64: [QK | DK | QM | DM]
-  float* Ls = reinterpret_cast<float*>(smem + 2 * T128 + 8 * T64);   // [2][64] lse * log2e
-  float* Es = Ls + 128;                                              // [2][64] delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Es + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 8 * T64);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_empty = bars + 1;
   TRACE_DECL;
@@ -533,7 +530,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
     // query columns of a sub-tile; at the end of an item one half stores dV, the other dK.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;          // 0..255 among the softmax threads
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
@@ -879,7 +875,7 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + 1024 + 256 + 1024;
+  constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + 256 + 1024;
   constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + 256 + 1024;
   auto k1 = attn_bwd_dkv_tc_kernel<DH>;
   auto k2 = attn_bwd_dq_tc_kernel<DH>;

@@ -65,8 +65,13 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 
 // LayerNorm backward.  dx = rstd * (dy*g - mean(dy*g) - xh * mean(dy*g*xh)) [+ dres];
 // per-CTA partial sums of dgamma = sum dy*xh and dbeta = sum dy go to part[blk][2][D].
+// HBM-bound (reads dy, x, dres; writes dx).  One warp per row; what limits the stream is how many bytes a
+// warp keeps in flight, i.e. registers: the column accumulators therefore live in the warp's private
+// shared-memory slab (conflict-free float4 read-modify-write per row), which leaves the register file to
+// the row being loaded, and the dres row is requested together with x and dy so a row costs one HBM
+// round trip, not two.
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
               float* __restrict__ dx, float* __restrict__ part, int M, int D, int round_out) {
@@ -74,61 +79,65 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 2;
-  float4 dg[NV], db[NV];
+  float4* acc_g = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D);
+  float4* acc_b = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D + D);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) { acc_g[c] = zero4; acc_b[c] = zero4; }
+  }
   for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
     const float4* gr = reinterpret_cast<const float4*>(dy + (size_t)row * D);
+    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * D) : nullptr;
+    float4 xh[NV], g[NV], r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {          // all of the row's HBM requests go out back to back
+      const int c = lane + i * 32;
+      xh[i] = zero4; g[i] = zero4; r[i] = zero4;
+      if (c < nv) {
+        xh[i] = xr[c];
+        g[i] = gr[c];
+        if (rr) r[i] = rr[c];
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[NV], g[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
-        const float4 xv = xr[c];
-        const float4 d = gr[c];
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-      } else {
-        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g[i] = xh[i];
+        const float4 d = g[i];
+        const float4 h = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
+        float4 ag = acc_g[c], ab = acc_b[c];
+        ag.x += d.x * h.x; ag.y += d.y * h.y; ag.z += d.z * h.z; ag.w += d.w * h.w;
+        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+        acc_g[c] = ag; acc_b[c] = ab;
+        const float4 t = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += (t.x + t.y) + (t.z + t.w);
+        s2 += (t.x * h.x + t.y * h.y) + (t.z * h.z + t.w * h.w);
+        xh[i] = h; g[i] = t;
       }
     }
     const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
     float4* outr = reinterpret_cast<float4*>(dx + (size_t)row * D);
-    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * D) : nullptr;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
-        o.x = rs * (g[i].x - m1 - xh[i].x * m2);
-        o.y = rs * (g[i].y - m1 - xh[i].y * m2);
-        o.z = rs * (g[i].z - m1 - xh[i].z * m2);
-        o.w = rs * (g[i].w - m1 - xh[i].w * m2);
-        if (rr) { const float4 r = rr[c]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+        o.x = rs * (g[i].x - m1 - xh[i].x * m2) + r[i].x;
+        o.y = rs * (g[i].y - m1 - xh[i].y * m2) + r[i].y;
+        o.z = rs * (g[i].z - m1 - xh[i].z * m2) + r[i].z;
+        o.w = rs * (g[i].w - m1 - xh[i].w * m2) + r[i].w;
         if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         outr[c] = o;
       }
     }
   }
   // CTA-level reduction of the per-warp column partials
-  float* sg = sm + (size_t)warp * 2 * D;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane + i * 32;
-    if (c < nv) {
-      reinterpret_cast<float4*>(sg)[c] = dg[i];
-      reinterpret_cast<float4*>(sg + D)[c] = db[i];
-    }
-  }
   __syncthreads();
   for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
     float a = 0.f;

@@ -208,7 +208,8 @@ def g_rowwise():
     ms = time_ms(lambda: ops.layernorm_fwd(x, g, b, True))
     print(f"ln fwd perf: {ms:.3f} ms {2*M*D*4/ms/1e6:.0f} GB/s")
     y, mean, rstd = ops.layernorm_fwd(x, g, b, True)
-    ms = time_ms(lambda: ops.layernorm_bwd(y, x, mean, rstd, g, y))
+    dy = torch.randn_like(x); dres = torch.randn_like(x)
+    ms = time_ms(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dres))
     print(f"ln bwd perf: {ms:.3f} ms {4*M*D*4/ms/1e6:.0f} GB/s")
     ms = time_ms(lambda: ops.colsum(x))
     print(f"colsum perf: {ms:.3f} ms {M*D*4/ms/1e6:.0f} GB/s")

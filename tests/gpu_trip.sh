@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 60 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "(attention and (16 or 24 or 130)) or (gemm_nt and 64) or vq_matches or gemm_epilogues" > gpurun_out/sanitizer_racecheck_full.txt 2>&1
-grep -E "Race reported|Error:|Warning:|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_racecheck_full.txt | sed 's/=========//' | cut -c1-260 | sort | uniq -c | sort -rn | head -30
+timeout 300 python tests/gpu_probe.py rowwise 2>&1 | tail -14
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_ -c 6 -o gpurun_out/prof_ln -f python tests/ncu_target.py ln > gpurun_out/ncu_ln.log 2>&1; tail -2 gpurun_out/ncu_ln.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
