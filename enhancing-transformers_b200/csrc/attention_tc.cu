@@ -21,22 +21,29 @@
 
 namespace b200 {
 
-// Development trace (compiled only with -DB200_ATTN_TRACE into a separate .so): block 0 of the dQ
-// kernel logs (event id, clock64) pairs of its MMA warp and of one softmax warp.
+// Development trace (compiled only with -DB200_ATTN_TRACE into a separate .so, `make trace`): block 0 of
+// the forward and dKV kernels logs (event id, clock64) pairs of three warps into a small shared-memory
+// ring (global-memory logging costs ~500 cycles per event and hides what is being measured).
 #ifdef B200_ATTN_TRACE
-__device__ long long g_trace[3 * 1024];
-// per-role trace rings in shared memory (no atomics, ~10 cycles per event); role r logs (event, clock) pairs
-#define TRACE_DECL __shared__ long long tr_buf[3][1024]; int tr_n = 0
+#ifndef B200_TRACE_SKIP
+#define B200_TRACE_SKIP 300          // events to let pass before recording (steady state, past the first items)
+#endif
+constexpr int kTraceCap = 36;        // events kept per role: the dKV kernel has < 2 KB of shared memory to spare
+__device__ long long g_trace[3 * 2 * kTraceCap];
+#define TRACE_DECL                                                                                \
+  __shared__ long long tr_buf[3][2 * kTraceCap]; int tr_n = 0;                                    \
+  for (int i_ = threadIdx.x; i_ < 3 * 2 * kTraceCap; i_ += blockDim.x) (&tr_buf[0][0])[i_] = 0
 #define TRACE(role, ev)                                                                           \
   do {                                                                                            \
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 511) {                              \
-      tr_buf[role][2 * tr_n] = (ev); tr_buf[role][2 * tr_n + 1] = clock64(); ++tr_n;             \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                             \
+      const int k_ = tr_n++ - B200_TRACE_SKIP;                                                    \
+      if (k_ >= 0 && k_ < kTraceCap) { tr_buf[role][2 * k_] = (ev); tr_buf[role][2 * k_ + 1] = clock64(); } \
     }                                                                                             \
   } while (0)
 #define TRACE_DUMP()                                                                              \
   do {                                                                                            \
     __syncthreads();                                                                              \
-    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 1024; i_ += blockDim.x) g_trace[i_] = tr_buf[i_ / 1024][i_ % 1024]; \
+    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 2 * kTraceCap; i_ += blockDim.x) g_trace[i_] = (&tr_buf[0][0])[i_]; \
   } while (0)
 #else
 #define TRACE_DECL
@@ -56,6 +63,31 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]) 
 __device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory"); }
 constexpr float kLog2eF = 1.4426950408889634f;
 
+constexpr int kOutBoxBytes = 8 * 4096;   // one 32-row x 128-byte store box per softmax warp
+
+// One warp stores 32 rows x 32 fp32 columns (lane = row, values r[0..31]) with a single TMA store:
+// registers -> 128B-swizzled 4 KB smem box -> cp.async.bulk.tensor, so HBM sees whole 128-byte lines and
+// rows / columns past the tensor edge are clipped.  (A thread writing its own row straight to global
+// memory makes every store instruction touch 32 different lines; at the end of a work item that
+// serialises in the L1 store path for thousands of cycles and back-pressures the mbarrier traffic of
+// the TMA / MMA warps.)
+__device__ __forceinline__ void warp_store_box(uint8_t* box, const CUtensorMap* tm, const float (&r)[32], int c0, int c1, int c2,
+                                               int lane) {
+  if (lane == 0) bulk_wait_group_read<0>();   // the box's previous store has been read out
+  __syncwarp();
+  uint8_t* rowp = box + lane * 128;
+  const uint32_t swz = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(rowp + ((j ^ swz) << 4)) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, box, c0, c1, c2);
+    bulk_commit_group();
+  }
+}
+
 struct AttnTcParams {
   float* out;        // [B*N, heads*DH]
   float* lse;        // [B*heads*N]
@@ -67,7 +99,8 @@ struct AttnTcParams {
 
 template <int DH>
 __global__ void __launch_bounds__(kAtcThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
   constexpr int KB = DH / 32;                 // 128-byte k-blocks per row
   constexpr int TILE_BYTES = 128 * DH * 4;    // one Q / K / V tile
   constexpr int KBLK_BYTES = 128 * 128;       // one k-block (or one MN atom of V): 128 rows x 128 B
@@ -76,7 +109,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + TILE_BYTES;            // [2]
   uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint8_t* obox = smem + 5 * TILE_BYTES;      // [8 softmax warps][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;    // [2]
@@ -90,6 +124,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   uint64_t* sfree = bars + 18;    // [2] S/P buffer consumed by the P.V MMAs (issuer B -> issuer A)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
+  TRACE_DECL;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -184,9 +219,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       for (int j = 0; j < T; ++j, ++pv_it) {
         const int s = pv_it & 1;
         const uint32_t ph = (pv_it >> 1) & 1;
+        TRACE(2, 103);
         mbar_wait(&v_full[s], ph);
         mbar_wait(&o_empty[s], ph ^ 1);
+        TRACE(2, 105);
         mbar_wait(&p_full[s], ph);
+        TRACE(2, 104);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
@@ -198,6 +236,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           umma_commit<1>(&sfree[s]);
         }
         __syncwarp();
+        TRACE(2, 106);
       }
     }
   } else {
@@ -235,7 +274,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       };
       for (int j = 0; j < T; ++j, ++t_it) {
         const int s = t_it & 1;
+        if (warp == 2) TRACE(0, 200); else if (warp == 6) TRACE(1, 200);
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        if (warp == 2) TRACE(0, 220); else if (warp == 6) TRACE(1, 220);
         tcgen05_fence_after();
         const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
         const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
@@ -244,6 +285,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         tmem_ld_32x32(sa, v0);
         tmem_ld_32x32(sa + 32, v1);
         tmem_ld_wait();
+        if (warp == 2) TRACE(0, 230); else if (warp == 6) TRACE(1, 230);
         if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -254,11 +296,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        if (warp == 2) TRACE(0, 240); else if (warp == 6) TRACE(1, 240);
         float* xs = xch + (t_it & 1) * 256;
         xs[half * 128 + row_in_tile] = mx;
         pair_bar(q);                                        // only the two warps that share these rows
         mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
         const float m_new = fmaxf(m, mx);
+        if (warp == 2) TRACE(0, 250); else if (warp == 6) TRACE(1, 250);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
         float sum = 0.f, sum1 = 0.f;
@@ -271,16 +315,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           v1[i] = tf32_bits_for_mma(e1);
         }
         sum += sum1;
+        if (warp == 2) TRACE(0, 260); else if (warp == 6) TRACE(1, 260);
         tmem_st_32x32(sa, v0);
         tmem_st_32x32(sa + 32, v1);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (warp == 2) TRACE(0, 280); else if (warp == 6) TRACE(1, 280);
         l = fmaf(l, alpha, sum);
         if (j >= 1) accumulate_pv(t_it - 1, alpha_prev);
         alpha_prev = alpha;
         m = m_new;
+        if (warp == 2) TRACE(0, 290); else if (warp == 6) TRACE(1, 290);
       }
       accumulate_pv(t_it - 1, alpha_prev);
       float* ls = xch + 512;
@@ -288,8 +335,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       pair_bar(q);
       l += ls[(half ^ 1) * 128 + row_in_tile];
       const int row = qt * 128 + row_in_tile;
-      if (row < p.N) {
-        const float inv = 1.f / l;
+      const float inv = 1.f / l;
+      if constexpr (OC == 32) {
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
+        warp_store_box(obox + (warp - 2) * 4096, &tmO, o, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+      } else if (row < p.N) {
         float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
 #pragma unroll
         for (int i = 0; i < OC; i += 4) {
@@ -297,10 +348,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
           if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
           *reinterpret_cast<float4*>(op + i) = r;
         }
-        if (half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
       }
+      if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
       pair_bar(q);     // ls is rewritten by the next item only after the partner has read it
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -308,7 +360,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+  TRACE_DUMP();
 }
+
 
 template <int DH>
 static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, int round_out,
@@ -335,13 +389,21 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem = 5 * 128 * DH * 4 + 1024 + 512 + 3 * 256 * 4;
+  CUtensorMap tmO;
+  {
+    const unsigned long long dims[3] = {(unsigned long long)inner, (unsigned long long)N, (unsigned long long)B};
+    const unsigned long long strides[2] = {(unsigned long long)inner * 4, (unsigned long long)N * inner * 4};
+    const unsigned box[3] = {32, 32, 1};
+    int rc = make_tensor_map_f32(&tmO, out, 3, dims, strides, box, 0);
+    if (rc) return rc;
+  }
+  int grid = num_sms();
+  if (grid > p.total_items) grid = p.total_items;
+  constexpr int smem = 5 * 128 * DH * 4 + kOutBoxBytes + 512 + 3 * 256 * 4 + 1024;
   auto kern = attn_fwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
-  int grid = num_sms();
-  if (grid > p.total_items) grid = p.total_items;
-  kern<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, p);
+  kern<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_tc_kernel");
   return 0;
 }
@@ -374,7 +436,8 @@ template <int DH>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ64,
                        const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmQM,
-                       const __grid_constant__ CUtensorMap tmDOM, const AttnBwdParams p) {
+                       const __grid_constant__ CUtensorMap tmDOM, const __grid_constant__ CUtensorMap tmOut,
+                       const AttnBwdParams p) {
   constexpr int KB = DH / 32;
   constexpr int T128 = 128 * DH * 4;   // K or V tile
   constexpr int T64 = 64 * DH * 4;     // one 64-row operand copy
@@ -384,7 +447,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   uint8_t* Ks = smem;
   uint8_t* Vs = smem + T128;
   uint8_t* St = smem + 2 * T128;        // stage s at St + s*4*T64: [QK | DK | QM | DM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 8 * T64);
+  uint8_t* obox = smem + 2 * T128 + 8 * T64;   // [8 softmax warps][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_empty = bars + 1;
   TRACE_DECL;
@@ -472,8 +536,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
         const uint32_t ph = (sd_it >> 1) & 1;
+        TRACE(0, 100);
         mbar_wait(&qk_full[s], ph);
+        TRACE(0, 107);
         mbar_wait(&sfree[s], ph ^ 1);
+        TRACE(0, 101);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qd = desc_advance(qd0, s * 4 * T64);
@@ -493,6 +560,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(kv_empty);
         }
         __syncwarp();
+        TRACE(0, 102);
       }
     }
   } else if (warp == kIssuerB) {
@@ -504,9 +572,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       for (int i = 0; i < NS; ++i, ++dv_it) {
         const int s = dv_it & 1;
         const uint32_t ph = (dv_it >> 1) & 1;
+        TRACE(1, 103);
         mbar_wait(&qm_full[s], ph);
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        TRACE(1, 105);
         mbar_wait(&p_full[s], ph);
+        TRACE(1, 104);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qmd = desc_advance(qmd0, s * 4 * T64);
@@ -523,6 +594,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
         __syncwarp();
+        TRACE(1, 106);
       }
     }
   } else {
@@ -589,29 +661,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       // item epilogue: this thread's key row of dV (half 0) or dK (half 1)
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
-      const int key = kt * 128 + q * 32 + lane;
-      const long long ld = 3ll * inner;
-      float* dst = p.dqkv + ((long long)b * p.N + key) * ld + (half == 0 ? 2 * inner : inner) + h * DH;
+      const int col0 = (half == 0 ? 2 * inner : inner) + h * DH;
       const float mul = half == 0 ? 1.f : p.scale;
 #pragma unroll 1
       for (int cc = 0; cc < DH / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_off + (half == 0 ? 256 : 320) + cc * 32, v);
         tmem_ld_wait();
-        if (key < p.N) {
+        float r[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 a = make_float4(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul, __uint_as_float(v[j + 2]) * mul,
-                                   __uint_as_float(v[j + 3]) * mul);
-            if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
-            *reinterpret_cast<float4*>(dst + cc * 32 + j) = a;
-          }
-        }
+        for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * mul) : __uint_as_float(v[j]) * mul;
+        warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, col0 + cc * 32, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
   }
   TRACE_DUMP();
   tcgen05_fence_before();
@@ -626,7 +692,7 @@ template <int DH>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
                       const __grid_constant__ CUtensorMap tmKV64, const __grid_constant__ CUtensorMap tmKM,
-                      const AttnBwdParams p) {
+                      const __grid_constant__ CUtensorMap tmOut, const AttnBwdParams p) {
   constexpr int KB = DH / 32;
   constexpr int T128 = 128 * DH * 4;
   constexpr int T64 = 64 * DH * 4;
@@ -636,7 +702,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   uint8_t* Qs = smem;
   uint8_t* Ds = smem + T128;
   uint8_t* St = smem + 2 * T128;        // stage s at St + s*3*T64: [KK | VK | KM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T128 + 6 * T64);
+  uint8_t* obox = smem + 2 * T128 + 6 * T64;   // [8 softmax warps][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* kk_full = bars + 2;    // [2]
@@ -819,7 +886,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         uint32_t v[OC];
         tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, v);
         tmem_ld_wait();
-        if (row < p.N) {
+        if constexpr (OC == 32) {
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * p.scale) : __uint_as_float(v[j]) * p.scale;
+          warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+        } else if (row < p.N) {
 #pragma unroll
           for (int j = 0; j < OC; j += 4) {
             float4 a = make_float4(__uint_as_float(v[j]) * p.scale, __uint_as_float(v[j + 1]) * p.scale,
@@ -833,6 +905,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -862,8 +935,9 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
                               int N, int heads, float scale, int round_out, cudaStream_t stream) {
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
-  CUtensorMap tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmDO128;
+  CUtensorMap tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmDO128, tmOut;
   int rc;
+  if ((rc = make_kmajor_map(&tmOut, dqkv, ld, N, B, 32))) return rc;
   if ((rc = make_kmajor_map(&tmKV128, qkv, ld, N, B, 128))) return rc;
   if ((rc = make_kmajor_map(&tmQ64, qkv, ld, N, B, 64))) return rc;
   if ((rc = make_kmajor_map(&tmDO64, dout, inner, N, B, 64))) return rc;
@@ -875,8 +949,8 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale; p.round_out = round_out;
-  constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + 256 + 1024;
-  constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + 256 + 1024;
+  constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + kOutBoxBytes + 256 + 1024;
+  constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + kOutBoxBytes + 256 + 1024;
   auto k1 = attn_bwd_dkv_tc_kernel<DH>;
   auto k2 = attn_bwd_dq_tc_kernel<DH>;
   static bool configured = false;
@@ -887,16 +961,16 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   }
   int grid = num_sms();
   if (grid > p.total_items) grid = p.total_items;
-  k1<<<grid, kAtcThreads, smem_kv, stream>>>(tmKV128, tmQ64, tmDO64, tmQM, tmDOM, p);
+  k1<<<grid, kAtcThreads, smem_kv, stream>>>(tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, p);
+  k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return 0;
 }
 
 #ifdef B200_ATTN_TRACE
-extern "C" int b200vq_trace_read(long long* out) {   // out[3][1024]: (event, clock) pairs per role, zero padded
-  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 1024);
+extern "C" int b200vq_trace_read(long long* out) {   // out[3][2 * 36]: (event, clock) pairs per role, zero padded
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace));
   return 0;
 }
 #endif

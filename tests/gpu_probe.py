@@ -410,14 +410,14 @@ def g_attn_trace():
     qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
     o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
     do = tf32_rn(torch.randn(B * N, inner, device="cuda"))
-    buf = (ctypes.c_longlong * (3 * 1024))()
+    buf = (ctypes.c_longlong * (3 * 72))()
     ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
     torch.cuda.synchronize()
     L.b200vq_trace_read(buf)
     ev = []
     for r in range(3):
-        for i in range(512):
-            e, t = buf[r * 1024 + 2 * i], buf[r * 1024 + 2 * i + 1]
+        for i in range(36):
+            e, t = buf[r * 72 + 2 * i], buf[r * 72 + 2 * i + 1]
             if t:
                 ev.append((t, r, e))
     ev.sort()
@@ -425,11 +425,45 @@ def g_attn_trace():
     names = {100: "wait k_full", 107: "got k, wait sfree", 101: "got sfree", 102: "issued S", 103: "wait v/o_empty", 105: "got them, wait p_full", 104: "got p_full", 250: "max exchanged", 290: "pv accumulated",
              106: "issued PV", 200: "wait s_full", 220: "got s_full", 240: "ld+max done", 260: "compute done", 280: "arrived p_full"}
     role = {0: "mmaA ", 1: "mmaB ", 2: "sm2  "}
-    start = next(i for i, (t, r, e) in enumerate(ev) if e in (100, 200) and i > len(ev) // 2)
+    start = 0
     prev = ev[start][0]
-    for t, r, e in ev[start:start + 56]:
+    for t, r, e in ev[start:start + 100]:
         print(f"{t - t0:9d} (+{t - prev:5d})  {role[r]}{names.get(e, e)}")
         prev = t
+
+
+def g_fwd_trace():
+    """timeline of the forward kernel's two partner softmax warps and issuer B (needs B200VQ_LIB=.../libb200vq_trace.so)"""
+    import ctypes
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    L = ctypes.CDLL(etb._lib.LIB_PATH)
+    B, N, heads, dh = 32, 1024, 12, 64
+    inner = heads * dh
+    qkv = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
+    for _ in range(3):
+        o, lse = ops.attention_fwd(qkv, B, N, heads, dh, 0.125, True)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * (3 * 72))()
+    L.b200vq_trace_read(buf)
+    ev = []
+    for r in range(3):
+        for i in range(36):
+            e, t = buf[r * 72 + 2 * i], buf[r * 72 + 2 * i + 1]
+            if t:
+                ev.append((t, r, e))
+    ev.sort()
+    t0 = ev[0][0]
+    names = {103: "wait v/o_empty", 105: "got them, wait p_full", 104: "got p_full", 106: "issued PV",
+             200: "wait s_full", 220: "got s_full", 230: "S loaded", 240: "max done", 250: "max exchanged", 260: "exp done",
+             280: "P stored + arrived", 290: "pv accumulated"}
+    role = {0: "smA  ", 1: "smB  ", 2: "mmaB "}
+    start = 0
+    last = {}
+    for t, r, e in ev[start:start + 90]:
+        print(f"{t - t0:9d} (+{t - last.get(r, t):5d})  {'      ' * r}{role[r]}{names.get(e, e)}")
+        last[r] = t
 
 
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
