@@ -19,11 +19,11 @@ _SIGNATURES = {
     "b200vq_arch": (ctypes.c_char_p, []),
     "b200vq_launch_count": (c_ll, []),
     "b200vq_gemm_tf32": (c_i, [c_f, c_ll, c_i, c_f, c_ll, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_ll, c_f, c_f, c_ll, c_i,
-                               c_f, c_ll, c_i, c_i, c_i, c_i, c_f]),
+                               c_f, c_ll, c_f, c_i, c_i, c_i, c_i, c_f]),
     "b200vq_splitk_reduce": (c_i, [c_f, c_i, c_ll, c_ll, c_f, c_f]),
     "b200vq_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "b200vq_layernorm_bwd_workspace_bytes": (c_sz, [c_i]),
-    "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
+    "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
     "b200vq_attention_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "b200vq_attention_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "b200vq_vq_workspace_bytes": (c_sz, [c_i, c_i, c_i]),

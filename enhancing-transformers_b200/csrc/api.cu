@@ -35,12 +35,12 @@ int num_sms() {
 
 // implemented in the other translation units
 int gemm_tf32(const float*, long long, int, const float*, long long, int, float*, long long, int, int, int, int, long long,
-              const float*, const float*, long long, int, const float*, long long, int, int, int, int, cudaStream_t);
+              const float*, const float*, long long, int, const float*, long long, float*, int, int, int, int, cudaStream_t);
 int splitk_reduce(const float*, int, long long, long long, float*, cudaStream_t);
 int layernorm_forward(const float*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
 size_t layernorm_bwd_workspace_bytes(int);
 int layernorm_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*,
-                       float*, int, int, int, void*, size_t, cudaStream_t);
+                       float*, float*, int, int, int, void*, size_t, cudaStream_t);
 int attention_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
 int attention_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float, int,
                        cudaStream_t);
@@ -70,10 +70,10 @@ long long b200vq_launch_count(void) { return g_launches.load(); }
 
 int b200vq_gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major, float* C,
                      long long ldc, int M, int N, int K, int splits, long long c_split_stride, const float* bias,
-                     const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux, int act,
-                     int round_out, int cta_group, int bn, void* stream) {
+                     const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux,
+                     float* colsum_part, int act, int round_out, int cta_group, int bn, void* stream) {
   return gemm_tf32(A, lda, a_major, B, ldb, b_major, C, ldc, M, N, K, splits, c_split_stride, bias, res, ldres, res_row_mod,
-                   aux, ldaux, act, round_out, cta_group, bn, S(stream));
+                   aux, ldaux, colsum_part, act, round_out, cta_group, bn, S(stream));
 }
 int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, void* stream) {
   return splitk_reduce(part, splits, n, split_stride, out, S(stream));
@@ -84,9 +84,10 @@ int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 size_t b200vq_layernorm_bwd_workspace_bytes(int D) { return layernorm_bwd_workspace_bytes(D); }
 int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, float* dgamma, float* dbeta, int M, int D, int round_out,
-                         void* workspace, size_t ws_bytes, void* stream) {
-  return layernorm_backward(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, D, round_out, workspace, ws_bytes, S(stream));
+                         const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
+                         int round_out, void* workspace, size_t ws_bytes, void* stream) {
+  return layernorm_backward(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, dxsum, M, D, round_out, workspace, ws_bytes,
+                            S(stream));
 }
 int b200vq_attention_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
                          int round_out, void* stream) {

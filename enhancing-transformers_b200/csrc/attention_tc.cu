@@ -259,10 +259,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 #pragma unroll
       for (int i = 0; i < OC; ++i) o[i] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-      auto accumulate_pv = [&](uint32_t it, float alpha) {
+      // fold the P.V partial product of tile `it` into the running output (its barrier has been waited on)
+      auto fold_pv = [&](uint32_t it, float alpha) {
         const int sp = it & 1;
-        mbar_wait(&o_full[sp], (it >> 1) & 1);
-        tcgen05_fence_after();
         uint32_t v[OC];
         tmem_ld_cols<OC>(tmem_base + lane_off + 256 + sp * 64 + half * OC, v);
         tmem_ld_wait();
@@ -272,19 +271,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[sp]);
       };
+      // the thread's 64 scores of a tile stay in registers between the max and the exp pass; those of tile
+      // j+1 are requested as soon as P_j has been handed over, so the TMEM load overlaps the P.V fold below
+      uint32_t v0[32], v1[32];
+      if (warp == 2) TRACE(0, 200); else if (warp == 6) TRACE(1, 200);
+      mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
+      tcgen05_fence_after();
+      {
+        const uint32_t s0 = tmem_base + lane_off + (t_it & 1) * 128 + half * 64;
+        tmem_ld_32x32(s0, v0);
+        tmem_ld_32x32(s0 + 32, v1);
+      }
+      tmem_ld_wait();
       for (int j = 0; j < T; ++j, ++t_it) {
         const int s = t_it & 1;
-        if (warp == 2) TRACE(0, 200); else if (warp == 6) TRACE(1, 200);
-        mbar_wait(&s_full[s], (t_it >> 1) & 1);
-        if (warp == 2) TRACE(0, 220); else if (warp == 6) TRACE(1, 220);
-        tcgen05_fence_after();
         const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
         const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
-        // one pass over TMEM: the thread's 64 scores stay in registers between max and exp
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(sa, v0);
-        tmem_ld_32x32(sa + 32, v1);
-        tmem_ld_wait();
         if (warp == 2) TRACE(0, 230); else if (warp == 6) TRACE(1, 230);
         if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
 #pragma unroll
@@ -324,12 +326,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
         if (lane == 0) mbar_arrive(&p_full[s]);
         if (warp == 2) TRACE(0, 280); else if (warp == 6) TRACE(1, 280);
         l = fmaf(l, alpha, sum);
-        if (j >= 1) accumulate_pv(t_it - 1, alpha_prev);
+        const bool more = j + 1 < T;
+        const uint32_t ph_s = ((t_it + 1) >> 1) & 1, ph_o = ((t_it - 1) >> 1) & 1;   // both live in buffer s ^ 1
+        if (more && j >= 1) mbar_wait2(&s_full[s ^ 1], ph_s, &o_full[s ^ 1], ph_o);
+        else if (more)      mbar_wait(&s_full[s ^ 1], ph_s);
+        else if (j >= 1)    mbar_wait(&o_full[s ^ 1], ph_o);
+        tcgen05_fence_after();
+        if (warp == 2) TRACE(0, 220); else if (warp == 6) TRACE(1, 220);
+        if (more) {
+          const uint32_t sn = tmem_base + lane_off + (s ^ 1) * 128 + half * 64;
+          tmem_ld_32x32(sn, v0);
+          tmem_ld_32x32(sn + 32, v1);
+        }
+        if (j >= 1) fold_pv(t_it - 1, alpha_prev);
+        else        tmem_ld_wait();
         alpha_prev = alpha;
         m = m_new;
         if (warp == 2) TRACE(0, 290); else if (warp == 6) TRACE(1, 290);
       }
-      accumulate_pv(t_it - 1, alpha_prev);
+      mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
+      tcgen05_fence_after();
+      fold_pv(t_it - 1, alpha_prev);
       float* ls = xch + 512;
       ls[half * 128 + row_in_tile] = l;
       pair_bar(q);

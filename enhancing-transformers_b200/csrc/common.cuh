@@ -136,6 +136,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Non-blocking probe of a phase parity (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Wait on two barriers whose probes are issued back to back, so their shared-memory round trips overlap
+// (a single probe costs a few hundred cycles while tcgen05.mma operand fetches saturate shared memory).
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const bool da = mbar_test(a, pa);
+  const bool db = mbar_test(b, pb);
+  if (!da) mbar_wait(a, pa);
+  if (!db) mbar_wait(b, pb);
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, completion on an mbarrier
 // ------------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ struct GemmParams {
   int in_mode;                 // 0 none, 1: + tile of tmIn (residual), 2: * (1 - tile^2) (tanh backward)
   int act;                     // 0 none, 1 tanh
   int round_out;               // 1: round the stored value to tf32 (it only feeds another GEMM)
+  float* colsum_part;          // null, or [ceil(M/32)][N]: column sums of every 32-row group of the stored C
 };
 
 constexpr int kBM = 128;
@@ -233,13 +234,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint8_t* inb = in_buf + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const float4*>(inb + ((j ^ swz) << 4));
-          __syncwarp();            // every lane holds its inputs: the buffer can be refilled
-          if (lane == 0 && c + 2 < NCHUNK) {
+        }
+        tmem_ld_wait();
+        if (tma_in) {   // placed after the TMEM wait so that the stall on the loads below is already paid for
+          // The refill below overwrites in_buf through the async proxy, so every lane's loads of this chunk must
+          // have *completed*, not merely issued: while tcgen05.mma operand fetches saturate shared memory a
+          // load can stay in flight longer than a TMA round trip (seen as one stale 16-byte group per few
+          // thousand tiles).  The ballot consumes a loaded register of every 16-byte group of every lane, and
+          // the refill is control-dependent on its result (which is never 0 in practice).
+          uint32_t bits = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bits |= __float_as_uint(a[j].x);
+          const uint32_t landed = __ballot_sync(0xffffffffu, bits != 0x7fc0deadu);
+          if (lane == 0 && c + 2 < NCHUNK && landed != 0u) {
             mbar_arrive_expect_tx(in_full, 4096);
             tma_load_2d(in_buf, &tmIn, in_full, col0 + 64, row0);
           }
         }
-        tmem_ld_wait();
         // the staging buffer must have been read by the TMA store of this warp's previous chunk
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
@@ -273,6 +284,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
           if (col0 < p.N && row0 < p.M) tma_store_3d(&tmC, out_buf, col0, row0, z);
           bulk_commit_group();
+        }
+        if (p.colsum_part) {
+          // bias gradient for free: lane c sums column c of the 32 x 32 box just staged (rows past M hold
+          // epilogue constants and are skipped); the row-group partials are reduced by a colsum launch
+          const int rmax = p.M - row0;
+          const uint8_t* colp = out_buf + ((lane & 3) << 2);
+          const uint32_t cj = lane >> 2;
+          float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 8) {       // 8 rows = one swizzle period; kept rolled so the 32 addresses are not hoisted
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+              if (rb + k < rmax) cs0 += *reinterpret_cast<const float*>(colp + (rb + k) * 128 + ((cj ^ k) << 4));
+              if (rb + k + 1 < rmax) cs1 += *reinterpret_cast<const float*>(colp + (rb + k + 1) * 128 + ((cj ^ (k + 1)) << 4));
+            }
+          }
+          if (col0 + lane < p.N && row0 < p.M) p.colsum_part[(size_t)(row0 >> 5) * p.N + col0 + lane] = cs0 + cs1;
         }
       }
       tcgen05_fence_before();
@@ -432,8 +460,9 @@ static int dispatch_major(int am, int bm, const CUtensorMap& a, const CUtensorMa
 
 int gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major, float* C,
               long long ldc, int M, int N, int K, int splits, long long c_split_stride, const float* bias,
-              const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux, int act,
-              int round_out, int cta_group, int bn, cudaStream_t stream) {
+              const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux,
+              float* colsum_part, int act, int round_out, int cta_group, int bn, cudaStream_t stream) {
+  B200_CHECK_ARG(!colsum_part || splits == 1, "gemm: colsum_part cannot be combined with split-K");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits > 0, "gemm: empty problem M=%d N=%d K=%d splits=%d", M, N, K, splits);
   B200_CHECK_ARG(N % 4 == 0 && ldc % 4 == 0, "gemm: N and ldc must be multiples of 4 (N=%d ldc=%lld)", N, ldc);
   B200_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "gemm: lda/ldb must be multiples of 4 floats (16-byte TMA strides)");
@@ -456,7 +485,7 @@ int gemm_tf32(const float* A, long long lda, int a_major, const float* B, long l
   p.k_blocks = (K + kBK - 1) / kBK;
   p.C = C; p.ldc = ldc; p.c_split_stride = c_split_stride;
   B200_CHECK_ARG(!(aux && res && res_row_mod == 0), "gemm: residual and tanh' inputs cannot be combined");
-  p.bias = bias; p.act = act; p.round_out = round_out;
+  p.bias = bias; p.act = act; p.round_out = round_out; p.colsum_part = colsum_part;
   p.res = (res && res_row_mod > 0) ? res : nullptr; p.ldres = ldres; p.res_row_mod = res_row_mod;
   p.in_mode = aux ? 2 : ((res && res_row_mod == 0) ? 1 : 0);
 

@@ -64,28 +64,34 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // LayerNorm backward.  dx = rstd * (dy*g - mean(dy*g) - xh * mean(dy*g*xh)) [+ dres];
-// per-CTA partial sums of dgamma = sum dy*xh and dbeta = sum dy go to part[blk][2][D].
+// per-CTA partial sums of dgamma = sum dy*xh and dbeta = sum dy go to part[blk][NACC][D]; with NACC == 3 the
+// column sums of the *output* dx are produced too (dx is the gradient arriving at the bias of the Linear that
+// fed this residual stream, reference layers.py:118 / :99-101, so its bias gradient needs no pass of its own).
 // HBM-bound (reads dy, x, dres; writes dx).  One warp per row; what limits the stream is how many bytes a
 // warp keeps in flight, i.e. registers: the column accumulators therefore live in the warp's private
 // shared-memory slab (conflict-free float4 read-modify-write per row), which leaves the register file to
 // the row being loaded, and the dres row is requested together with x and dy so a row costs one HBM
 // round trip, not two.
-template <int NV>
+template <int NV, int NACC>
 __global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
               float* __restrict__ dx, float* __restrict__ part, int M, int D, int round_out) {
-  extern __shared__ float sm[];   // [warps][2][D]
+  extern __shared__ float sm[];   // [warps][NACC][D]
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 2;
-  float4* acc_g = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D);
-  float4* acc_b = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D + D);
+  float4* acc_g = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D);
+  float4* acc_b = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D + D);
+  float4* acc_o = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D + 2 * D);   // used when NACC == 3
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
-    if (c < nv) { acc_g[c] = zero4; acc_b[c] = zero4; }
+    if (c < nv) {
+      acc_g[c] = zero4; acc_b[c] = zero4;
+      if (NACC == 3) acc_o[c] = zero4;
+    }
   }
   for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
@@ -134,15 +140,20 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         o.w = rs * (g[i].w - m1 - xh[i].w * m2) + r[i].w;
         if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         outr[c] = o;
+        if (NACC == 3) {
+          float4 ao = acc_o[c];
+          ao.x += o.x; ao.y += o.y; ao.z += o.z; ao.w += o.w;
+          acc_o[c] = ao;
+        }
       }
     }
   }
   // CTA-level reduction of the per-warp column partials
   __syncthreads();
-  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
+  for (int j = threadIdx.x; j < NACC * D; j += blockDim.x) {
     float a = 0.f;
-    for (int w = 0; w < warps_per_block; ++w) a += sm[(size_t)w * 2 * D + j];
-    part[(size_t)blockIdx.x * 2 * D + j] = a;
+    for (int w = 0; w < warps_per_block; ++w) a += sm[(size_t)w * NACC * D + j];
+    part[(size_t)blockIdx.x * NACC * D + j] = a;
   }
 }
 
@@ -155,14 +166,16 @@ __global__ void colpart_reduce_kernel(const float* __restrict__ part, int nparts
   out[j] = a;
 }
 
-// part is [nparts][2][D] -> dgamma[D], dbeta[D]
-__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+// part is [nparts][nacc][D] -> dgamma[D], dbeta[D] (, dxsum[D])
+__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, int nacc, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ dxsum) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * D) return;
+  if (j >= nacc * D) return;
   float a = 0.f;
-  for (int i = 0; i < nparts; ++i) a += part[(size_t)i * 2 * D + j];
-  if (j < D) dgamma[j] = a; else dbeta[j - D] = a;
+  for (int i = 0; i < nparts; ++i) a += part[(size_t)i * nacc * D + j];
+  if (j < D) dgamma[j] = a;
+  else if (j < 2 * D) dbeta[j - D] = a;
+  else dxsum[j - 2 * D] = a;
 }
 
 // column sums of X[M, N] (bias gradients): stage 1 writes part[blockIdx.y][N].
@@ -318,37 +331,44 @@ int layernorm_forward(const float* x, const float* gamma, const float* beta, flo
 }
 
 int layernorm_bwd_blocks() { return num_sms() * 2; }
-size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)layernorm_bwd_blocks() * 2 * D * sizeof(float); }
+size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)layernorm_bwd_blocks() * 3 * D * sizeof(float); }
 
-template <int NV>
+template <int NV, int NACC>
 static int ln_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* dres, float* dx, float* part, int M, int D, int round_out, int blocks, cudaStream_t s) {
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  auto kern = ln_bwd_kernel<NV>;
+  const size_t smem = (size_t)8 * NACC * D * sizeof(float);
+  auto kern = ln_bwd_kernel<NV, NACC>;
   if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, 256, smem, s>>>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out);
   return 0;
 }
 
+template <int NACC>
+static int ln_bwd_dispatch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* dres, float* dx, float* part, int M, int D, int round_out, int blocks, cudaStream_t s) {
+  const int nv = (D + 127) / 128;
+  if (nv <= 1) return ln_bwd_launch<1, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  if (nv <= 2) return ln_bwd_launch<2, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  if (nv <= 4) return ln_bwd_launch<4, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  if (nv <= 6) return ln_bwd_launch<6, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  if (nv <= 10) return ln_bwd_launch<10, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  return ln_bwd_launch<16, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+}
+
 int layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       const float* dres, float* dx, float* dgamma, float* dbeta, int M, int D, int round_out,
+                       const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D, int round_out,
                        void* workspace, size_t ws_bytes, cudaStream_t stream) {
   B200_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm: need D %% 4 == 0 and D <= 2048 (D=%d)", D);
   B200_CHECK_ARG(ws_bytes >= layernorm_bwd_workspace_bytes(D), "layernorm_backward: workspace too small");
   int blocks = layernorm_bwd_blocks();
   if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
   float* part = static_cast<float*>(workspace);
-  const int nv = (D + 127) / 128;
-  int rc;
-  if (nv <= 1) rc = ln_bwd_launch<1>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
-  else if (nv <= 2) rc = ln_bwd_launch<2>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
-  else if (nv <= 4) rc = ln_bwd_launch<4>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
-  else if (nv <= 6) rc = ln_bwd_launch<6>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
-  else if (nv <= 10) rc = ln_bwd_launch<10>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
-  else rc = ln_bwd_launch<16>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  const int nacc = dxsum ? 3 : 2;
+  int rc = dxsum ? ln_bwd_dispatch<3>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream)
+                 : ln_bwd_dispatch<2>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
   if (rc) return rc;
   B200_LAUNCH_OK("ln_bwd_kernel");
-  ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, stream>>>(part, blocks, D, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(nacc * D + 255) / 256, 256, 0, stream>>>(part, blocks, D, nacc, dgamma, dbeta, dxsum);
   B200_LAUNCH_OK("ln_param_reduce_kernel");
   return 0;
 }

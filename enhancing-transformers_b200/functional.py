@@ -11,6 +11,8 @@ changes."""
 from __future__ import annotations
 
 
+import os
+
 import torch
 
 from . import ops
@@ -56,6 +58,27 @@ def _wgrad(dy: Tensor, x: Tensor, rows: int, cols: int) -> Tensor:
     return ops.splitk_reduce(part) if splits > 1 else part
 
 
+GEMM_COLSUM = os.environ.get("B200VQ_GEMM_COLSUM", "1") != "0"   # bias-gradient column sums from the dgrad epilogue
+_COLSUM_ATTR = "_b200vq_colsum"
+
+
+def _attach_colsum(t: torch.Tensor, colsum: torch.Tensor) -> torch.Tensor:
+    """Remember the column sums of a gradient tensor the LayerNorm-backward kernel produced for free.
+    The next backward node down the residual stream needs exactly colsum(t) for a bias gradient; it
+    picks the value up with `_colsum_of` if (and only if) the very same, unmodified tensor reaches it."""
+    setattr(t, _COLSUM_ATTR, (colsum, t._version, t.data_ptr()))
+    return t
+
+
+def _colsum_of(t: torch.Tensor) -> torch.Tensor:
+    tag = getattr(t, _COLSUM_ATTR, None)
+    if tag is not None:
+        colsum, version, ptr = tag
+        if version == t._version and ptr == t.data_ptr() and colsum.shape[0] == t.shape[-1]:
+            return colsum
+    return ops.colsum(t)
+
+
 class TransformerLayerFn(torch.autograd.Function):
     """x -> attn(LN(x)) + x -> ff(LN(.)) + .   (reference layers.py:145-148 with :85-132)"""
 
@@ -89,17 +112,20 @@ class TransformerLayerFn(torch.autograd.Function):
         scale = dh ** -0.5
         g = g.contiguous()
         # ---- feed-forward branch
-        db2 = ops.colsum(g)
+        db2 = _colsum_of(g)          # free when g came out of a LayerNorm-backward kernel (next block / final norm)
         dw2 = _wgrad(g, t, D, mlp)
-        dt = ops.gemm(g, w2r, M, mlp, D, b_major=1, aux=t, round_out=True, cta_group=cg)     # (g W2) * (1 - t^2)
-        db1 = ops.colsum(dt)
+        if GEMM_COLSUM:
+            dt, db1 = ops.gemm(g, w2r, M, mlp, D, b_major=1, aux=t, round_out=True, cta_group=cg,
+                               want_colsum=True)                                        # (g W2) * (1 - t^2), colsum(dt)
+        else:
+            dt = ops.gemm(g, w2r, M, mlp, D, b_major=1, aux=t, round_out=True, cta_group=cg)
+            db1 = ops.colsum(dt)
         dw1 = _wgrad(dt, h2, mlp, D)
         dh2 = ops.gemm(dt, w1r, M, D, mlp, b_major=1, cta_group=cg)
         del dt
-        g1, dln2_w, dln2_b = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2_w, g)
+        g1, dln2_w, dln2_b, dbo = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2_w, g, want_colsum=True)
         del dh2
-        # ---- attention branch
-        dbo = ops.colsum(g1)
+        # ---- attention branch (dbo = colsum(g1) came with the kernel above)
         dwo = _wgrad(g1, o, D, inner)
         do = ops.gemm(g1, wo, M, inner, D, b_major=1, round_out=True, cta_group=cg)
         dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, True)
@@ -107,7 +133,8 @@ class TransformerLayerFn(torch.autograd.Function):
         dwq = _wgrad(dqkv, h1, 3 * inner, D)
         dh1 = ops.gemm(dqkv, wq, M, D, 3 * inner, b_major=1, cta_group=cg)
         del dqkv
-        gx, dln1_w, dln1_b = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, g1)
+        gx, dln1_w, dln1_b, gx_sum = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, g1, want_colsum=True)
+        _attach_colsum(gx, gx_sum)
         return gx, dln1_w, dln1_b, dwq, dwo, dbo, dln2_w, dln2_b, dw1, db1, dw2, db2, None, None, None, None
 
 
@@ -123,7 +150,8 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, mean, rstd, w = ctx.saved_tensors
-        dx, dw, db = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, w, None)
+        dx, dw, db, dx_sum = ops.layernorm_bwd(g.contiguous(), x, mean, rstd, w, None, want_colsum=True)
+        _attach_colsum(dx, dx_sum)
         return dx, dw, db, None
 
 
@@ -202,7 +230,7 @@ class PatchEmbedFn(torch.autograd.Function):
         D = w.shape[0]
         M, pd = patches.shape
         g = g.contiguous()
-        db = ops.colsum(g)
+        db = _colsum_of(g)
         dw = _wgrad(g, patches, D, pd).view_as(w)
         dimg = None
         if ctx.needs_input_grad[0]:

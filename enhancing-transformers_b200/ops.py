@@ -41,8 +41,9 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_major: int = 0, b_ma
          lda: Optional[int] = None, ldb: Optional[int] = None, out: Optional[Tensor] = None,
          bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_row_mod: int = 0,
          aux: Optional[Tensor] = None, act: int = 0, round_out: bool = False, splits: int = 1,
-         cta_group: int = 1, bn: int = 0) -> Tensor:
-    """C[M,N] = epilogue(A . B^T).  See b200vq_gemm_tf32.  With splits > 1 returns [splits, M, N]."""
+         cta_group: int = 1, bn: int = 0, want_colsum: bool = False):
+    """C[M,N] = epilogue(A . B^T).  See b200vq_gemm_tf32.  With splits > 1 returns [splits, M, N].
+    want_colsum: also return colsum(C) (-> (C, colsum)); the epilogue emits per-32-row partial sums."""
     _req(a, "a"); _req(b, "b"); _req(bias, "bias"); _req(res, "res"); _req(aux, "aux")
     if lda is None:
         lda = a.shape[-1]
@@ -51,11 +52,14 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_major: int = 0, b_ma
     if out is None:
         out = torch.empty((splits, M, N) if splits > 1 else (M, N), device=a.device, dtype=torch.float32)
     _req(out, "out")
+    part = torch.empty((M + 31) // 32, N, device=a.device, dtype=torch.float32) if want_colsum else None
     rc = _lib.lib().b200vq_gemm_tf32(_p(a), lda, a_major, _p(b), ldb, b_major, _p(out), N, M, N, K, splits, M * N,
                                      _p(bias), _p(res), (res.shape[-1] if res is not None else 0), res_row_mod,
-                                     _p(aux), (aux.shape[-1] if aux is not None else 0), act, int(round_out),
+                                     _p(aux), (aux.shape[-1] if aux is not None else 0), _p(part), act, int(round_out),
                                      cta_group, bn, _stream())
     _lib.check(rc, "gemm_tf32")
+    if want_colsum:
+        return out, colsum(part)
     return out
 
 
@@ -94,7 +98,8 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, round_out: bool) -> Tu
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
-                  round_out: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+                  round_out: bool = False, want_colsum: bool = False):
+    """-> (dx, dgamma, dbeta) or, with want_colsum, (dx, dgamma, dbeta, colsum(dx))"""
     _req(dy, "dy"); _req(x, "x"); _req(dres, "dres")
     D = x.shape[-1]
     M = x.numel() // D
@@ -104,8 +109,11 @@ def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tens
     dx = torch.empty_like(x)
     dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
     dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
+    dxsum = torch.empty(D, device=x.device, dtype=torch.float32) if want_colsum else None
     _lib.check(L.b200vq_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma),
-                                      _p(dbeta), M, D, int(round_out), _p(ws), ws_bytes, _stream()), "layernorm_bwd")
+                                      _p(dbeta), _p(dxsum), M, D, int(round_out), _p(ws), ws_bytes, _stream()), "layernorm_bwd")
+    if want_colsum:
+        return dx, dgamma, dbeta, dxsum
     return dx, dgamma, dbeta
 
 

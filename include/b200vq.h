@@ -47,22 +47,27 @@ long long b200vq_launch_count(void);
  * Epilogue, in this order: + bias[N]; act (0 none, 1 tanh -- layers.py:100);
  * * (1 - aux^2) (tanh backward); + res[row % res_row_mod or row] (residual add layers.py:147-148
  * or positional table :179,:210); tf32 rounding.
+ * colsum_part (nullable, [ceil(M/32)][N], splits must be 1): receives the column sums of every 32-row group of
+ * the stored C -- summed over the groups (b200vq_colsum) they are the bias gradient of the Linear whose
+ * pre-activation gradient this GEMM produced (net.0, layers.py:99), without another pass over C.
  * cta_group: 1 = one CTA per 128 x bn tile, 2 = CTA pair per 256 x bn tile; bn in {0=auto,64,128,192,256}. */
 int b200vq_gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major,
                      float* C, long long ldc, int M, int N, int K, int splits, long long c_split_stride,
                      const float* bias, const float* res, long long ldres, int res_row_mod,
-                     const float* aux, long long ldaux, int act, int round_out, int cta_group, int bn,
-                     void* stream);
+                     const float* aux, long long ldaux, float* colsum_part, int act, int round_out, int cta_group,
+                     int bn, void* stream);
 int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, void* stream);
 
 /* ---- LayerNorm (nn.LayerNorm(dim), eps 1e-5: layers.py:88,143) ---------------------------------*/
 int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
                          int M, int D, int round_out, void* stream);
 size_t b200vq_layernorm_bwd_workspace_bytes(int D);
-/* dx = LN'(dy) (+ dres, the skip-connection gradient of layers.py:147-148) */
+/* dx = LN'(dy) (+ dres, the skip-connection gradient of layers.py:147-148).  dxsum (nullable, [D]) receives the
+ * column sums of dx: dx is also the gradient at the bias of the Linear that wrote this residual stream
+ * (to_out layers.py:118, net.2 layers.py:101), so that bias gradient costs no extra pass over dx. */
 int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, float* dgamma, float* dbeta, int M, int D, int round_out,
-                         void* workspace, size_t ws_bytes, void* stream);
+                         const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
+                         int round_out, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- attention core (layers.py:124-130): softmax(q k^T * scale) v, no mask -----------------------
  * qkv is the [B*N, 3*heads*dh] output of to_qkv (q | k | v thirds, head h at columns h*dh);

@@ -58,6 +58,33 @@ def test_gemm_epilogues(cg):
 
 
 @pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(512, 768, 256), (1000, 320, 96), (40, 64, 64), (4096, 3072, 128)])
+def test_gemm_epilogue_column_sums(cg, M, N, K):
+    """the epilogue's per-32-row partial column sums reduce to colsum of the *stored* C (ragged M and N included)"""
+    a, bs = tf32_rn(torch.randn(M, K, device="cuda")), tf32_rn(torch.randn(K, N, device="cuda"))
+    aux, bias = torch.tanh(torch.randn(M, N, device="cuda")), torch.randn(N, device="cuda")
+    c, cs = ops.gemm(a, bs, M, N, K, b_major=1, aux=aux, bias=bias, round_out=True, cta_group=cg, want_colsum=True)
+    assert torch.equal(c, ops.gemm(a, bs, M, N, K, b_major=1, aux=aux, bias=bias, round_out=True, cta_group=cg))
+    assert relerr(cs, c.double().sum(0)) < 1e-5
+
+
+def test_gemm_epilogue_input_refill_is_race_free():
+    """Regression: the epilogue's TMA refill of the tanh'/residual input box used to be ordered only against the
+    *issue* of the shared-memory loads of the previous box; with a short K loop (tensor cores saturating shared
+    memory) and a busier epilogue (column sums) ~10% of launches of this shape stored one stale 16-byte group."""
+    M, N, K = 4096, 3072, 128
+    for it in range(40):
+        a, bs = tf32_rn(torch.randn(M, K, device="cuda")), tf32_rn(torch.randn(K, N, device="cuda"))
+        aux, bias = torch.tanh(torch.randn(M, N, device="cuda")), torch.randn(N, device="cuda")
+        kw = dict(b_major=1, aux=aux, bias=bias, round_out=True, cta_group=2)
+        c1, _ = ops.gemm(a, bs, M, N, K, want_colsum=True, **kw)
+        c2 = ops.gemm(a, bs, M, N, K, **kw)
+        assert torch.equal(c1, c2), f"iteration {it}: {(c1 != c2).sum().item()} elements differ"
+    ref = ((a.double() @ bs.double()) + bias.double()) * (1 - aux.double() ** 2)
+    assert relerr(c1, ref) < 1e-3          # tf32-rounded output
+
+
+@pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 768, 3072), (256, 96, 160), (1024, 192, 768), (32, 64, 288)])
 def test_gemm_nn_dgrad_form(cg, M, N, K):
     a, bs = tf32_rn(torch.randn(M, K, device="cuda")), tf32_rn(torch.randn(K, N, device="cuda"))
@@ -107,6 +134,10 @@ def test_layernorm_fwd_bwd(M, D):
     assert relerr(dg, gr.grad) < 1e-5 and relerr(db, br.grad) < 1e-5
     yt, _, _ = ops.layernorm_fwd(x, g, b, True)
     assert torch.equal(yt, tf32_rn(y))
+    # the same kernel can hand back the column sums of its output (the bias gradient of the Linear upstream)
+    dx2, dg2, db2, dxs = ops.layernorm_bwd(dy, x, mean, rstd, g, dres, want_colsum=True)
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
+    assert relerr(dxs, dx.double().sum(0)) < 1e-5
 
 
 def test_layout_and_reduction_kernels():

@@ -162,3 +162,33 @@ def test_tf32_shadow_follows_parameter_identity_and_version():
     sd = {k: v.detach().cpu() for k, v in ff.state_dict().items()}
     ref = O.feed_forward(x.cpu(), sd["net.0.weight"], sd["net.0.bias"], sd["net.2.weight"], sd["net.2.bias"])
     assert relmax(y1.cpu(), ref) < 2e-3 and not torch.allclose(y0, y1)
+
+
+def test_bias_gradients_reuse_layernorm_backward_column_sums(monkeypatch):
+    """to_out / net.2 bias gradients are column sums of tensors a LayerNorm-backward kernel just wrote; they must
+    come from that kernel (no stand-alone colsum launch for them) and must equal the stand-alone result."""
+    import enhancing_transformers_b200 as etb
+    from enhancing_transformers_b200 import functional as Fn
+    torch.manual_seed(0)
+    enc = etb.ViTEncoder(32, 8, dim=64, depth=2, heads=2, mlp_dim=128, dim_head=32).cuda()
+    img = torch.rand(2, 3, 32, 32, device="cuda")
+
+    def grads(use_attached):
+        for p in enc.parameters():
+            p.grad = None
+        calls = []
+        real = Fn.ops.colsum
+        monkeypatch.setattr(Fn.ops, "colsum", lambda t: (calls.append(tuple(t.shape)), real(t))[1])
+        if not use_attached:
+            monkeypatch.setattr(Fn, "_attach_colsum", lambda t, c: t)
+        enc(img).square().mean().backward()
+        monkeypatch.undo()
+        return {n: p.grad.clone() for n, p in enc.named_parameters() if p.grad is not None}, calls
+
+    g_ref, calls_ref = grads(False)
+    g_new, calls_new = grads(True)
+    # per block: db1 (mlp wide) stays a colsum; db2 and dbo no longer are (dbo never, db2 when the tag survives autograd)
+    assert len(calls_new) < len(calls_ref)
+    assert sum(1 for c in calls_new if c[-1] == 64) <= 1      # only the patch-embedding bias may still need one
+    for n in g_ref:
+        assert torch.allclose(g_new[n], g_ref[n], rtol=1e-5, atol=1e-7), n
