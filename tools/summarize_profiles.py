@@ -52,6 +52,14 @@ HEADERS = {
     "ln": "# ln_fwd / ln_bwd kernels M=131072 D=768 (python tests/ncu_target.py ln)\n"
           "# algorithmic bytes: fwd 805 MB (read x, write y), bwd 1611 MB (read dy, x, dres; write dx)\n",
 }
+# captures that predate later kernel changes (the round's GPU budget ran out before they could be redone)
+STALE_NOTES = {
+    "attn": "# NOTE: this capture predates the TMA-store epilogues and the pipelined forward softmax (commit e159a95 and later).\n"
+            "#       Current per-launch times at B=128 from the round-end launch list (r01_launch_shares.txt): fwd 906 us, dKV 1505 us,\n"
+            "#       dQ 1261 us (this capture's build: 1223 / 2145 / 1387 us); at B=64 under CUDA events: fwd 0.445 ms, bwd 1.421 ms.\n",
+    "ln": "# NOTE: captured after the shared-memory-accumulator rewrite of ln_bwd but before the optional third accumulator\n"
+          "#       (colsum of dx); round-end launch list: ln_bwd 256 us in the training step (NACC=3 variant), ln_fwd 126 us.\n",
+}
 OUT_NAMES = {"gemm2": "ncu_gemm_cg2", "attn": "ncu_attention", "vq": "ncu_vq", "ln": "ncu_layernorm"}
 
 
@@ -71,7 +79,12 @@ def summarise_rep(tag: str, src: str, dst: str, rnd: str) -> None:
     seen = {}
     for r in rows:               # keep the LAST launch of each kernel (warm caches, steady clocks)
         seen[r[kcol]] = r
-    lines = [HEADERS[tag], "# source: ncu --set full --clock-control none --import-source on (report under gpurun_out/, summarised by tools/summarize_profiles.py; last launch of each kernel)\n"]
+    import datetime
+    when = datetime.datetime.utcfromtimestamp(os.path.getmtime(rep)).strftime("%Y-%m-%d %H:%MZ")
+    lines = [HEADERS[tag], f"# source: ncu --set full --clock-control none, captured {when} (report under gpurun_out/, summarised by "
+             "tools/summarize_profiles.py; last launch of each kernel)\n"]
+    if tag in STALE_NOTES:
+        lines.append(STALE_NOTES[tag])
     for name, r in seen.items():
         lines.append(f"\n## {name[:140]}\n")
         for m in METRICS:
