@@ -80,7 +80,7 @@ def summarise_rep(tag: str, src: str, dst: str, rnd: str) -> None:
     for r in rows:               # keep the LAST launch of each kernel (warm caches, steady clocks)
         seen[r[kcol]] = r
     import datetime
-    when = datetime.datetime.utcfromtimestamp(os.path.getmtime(rep)).strftime("%Y-%m-%d %H:%MZ")
+    when = datetime.datetime.fromtimestamp(os.path.getmtime(rep), datetime.timezone.utc).strftime("%Y-%m-%d %H:%MZ")
     lines = [HEADERS[tag], f"# source: ncu --set full --clock-control none, captured {when} (report under gpurun_out/, summarised by "
              "tools/summarize_profiles.py; last launch of each kernel)\n"]
     if tag in STALE_NOTES:
