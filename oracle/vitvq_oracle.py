@@ -26,7 +26,6 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 Tensor = torch.Tensor
 LN_EPS = 1e-5          # nn.LayerNorm default, reference layers.py:88,143
