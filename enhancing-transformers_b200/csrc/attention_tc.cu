@@ -52,7 +52,6 @@ __device__ long long g_trace[3 * 2 * kTraceCap];
 
 constexpr int kAtcThreads = 352;      // warp 0 TMA, warp 1 MMA issuer A, warps 2..9 softmax (two per TMEM lane quarter), warp 10 MMA issuer B
 constexpr int kIssuerB = 10;
-constexpr int kAtcSoftmaxThreads = 256;
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]) {
