@@ -18,6 +18,7 @@
 //               output lives in registers: o = o * alpha + (P_j V_j read back from TMEM).
 // TMEM columns: S/P buffers [0,128) [128,256), PV buffers [256,256+DH) [320,320+DH).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -932,6 +933,255 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_DQ=128):
+// dQ kernel with 128-key tiles.  An M=128 tf32 MMA instruction costs max(N/2, ~48) cycles, so the
+// 64-key sub-tiles of the kernel above pay 48 cycles for 32 cycles of math on every score MMA.  Here
+//     S  = Q K_j^T, dP = dO V_j^T          N = 128: 8 + 8 instructions x 64 cycles
+//     dQ += dS_j K_j                       K-dim 128: 16 instructions x 48 cycles     = 1792 cycles / 128 keys
+// against 2 x 1152 before.  TMEM: S [0,128) single-buffered (dead as soon as the softmax warps have loaded it:
+// `s_free`), dP/dS [128,256) / [256,384) double-buffered (released by the dQ MMAs: `dp_free`), dQ [384,448).
+// Shared memory: Q, dO (K-major) + ONE stage of K (K-major), V (K-major), K (MN-major); the stage's buffers are
+// released at different times (kk_empty after the score MMAs, km_empty after the dQ MMAs), so the loads of tile
+// j+1 still overlap the softmax of tile j.
+template <int DH>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attn_bwd_dq128_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
+                         const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmKM128,
+                         const __grid_constant__ CUtensorMap tmOut, const AttnBwdParams p) {
+  constexpr int KB = DH / 32;
+  constexpr int T128 = 128 * DH * 4;
+  constexpr int KBLK128 = 128 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ds = smem + T128;
+  uint8_t* KKs = smem + 2 * T128;       // K tile, K-major
+  uint8_t* VKs = smem + 3 * T128;       // V tile, K-major
+  uint8_t* KMs = smem + 4 * T128;       // K tile, MN-major
+  uint8_t* obox = smem + 5 * T128;      // [8 softmax warps][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kk_full = bars + 2;
+  uint64_t* kk_empty = bars + 3;
+  uint64_t* km_full = bars + 4;
+  uint64_t* km_empty = bars + 5;
+  uint64_t* s_full = bars + 6;     // [2] indexed by the dP buffer of the tile
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* dp_free = bars + 10;   // [2] dS buffer consumed by issuer B
+  uint64_t* s_free = bars + 12;    // S loaded into registers by all 8 softmax warps
+  uint64_t* acc_full = bars + 13;
+  uint64_t* acc_empty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmKV128); tma_prefetch_desc(&tmKM128);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    mbar_init(kk_full, 1); mbar_init(kk_empty, 1);
+    mbar_init(km_full, 1); mbar_init(km_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); mbar_init(&dp_free[s], 1); }
+    mbar_init(s_free, 8);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int T = p.tiles128;            // key tiles of 128
+
+  if (warp == 0) {
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * T128);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(Qs + kb * KBLK128, &tmQ128, q_full, h * DH + kb * 32, qt * 128, b);
+          tma_load_3d(Ds + kb * KBLK128, &tmDO128, q_full, h * DH + kb * 32, qt * 128, b);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const uint32_t ph = t_it & 1;
+        mbar_wait(kk_empty, ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kk_full, 2 * T128);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_3d(KKs + kb * KBLK128, &tmKV128, kk_full, inner + h * DH + kb * 32, j * 128, b);
+            tma_load_3d(VKs + kb * KBLK128, &tmKV128, kk_full, 2 * inner + h * DH + kb * 32, j * 128, b);
+          }
+        }
+        __syncwarp();
+        mbar_wait(km_empty, ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(km_full, T128);
+          tma_load_4d(KMs, &tmKM128, km_full, 0, j * 128, (inner + h * DH) / 32, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- issuer A: S = Q K^T, dP = dO V^T   (N = 128)
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+    const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
+    const uint64_t kkd = make_smem_desc(smem_u32(KKs), 16, 1024, kLayoutSw128);
+    const uint64_t vkd = make_smem_desc(smem_u32(VKs), 16, 1024, kLayoutSw128);
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        mbar_wait(kk_full, t_it & 1);
+        mbar_wait(s_free, (t_it & 1) ^ 1);                 // S of the previous tile is in registers
+        mbar_wait(&dp_free[s], ((t_it >> 1) & 1) ^ 1);     // dS of tile t_it-2 consumed by the dQ MMAs
+        tcgen05_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t off = (k >> 2) * KBLK128 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base, desc_advance(qd, off), desc_advance(kkd, off), idesc_s, k != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t off = (k >> 2) * KBLK128 + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + 128 + s * 128, desc_advance(dd, off), desc_advance(vkd, off), idesc_s, k != 0);
+          }
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(kk_empty);
+          if (j == T - 1) umma_commit<1>(q_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: dQ += dS K (A operand from TMEM, K-dim = 128 keys)
+    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t kmd = make_smem_desc(smem_u32(KMs), KBLK128, 512, kLayoutSw128Base32);
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        mbar_wait(km_full, t_it & 1);
+        if (j == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        mbar_wait(&p_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t acc_on = j > 0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_tf32_ts(tmem_base + 384, tmem_base + 128 + s * 128 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
+          umma_commit<1>(km_empty);
+          umma_commit<1>(&dp_free[s]);
+          if (j == T - 1) umma_commit<1>(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // softmax warps: thread = query row, warps w and w+4 split the 128 key columns of a tile in halves of 64,
+    // each processed in two passes of 32 columns (register budget)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int row = qt * 128 + q * 32 + lane;
+      const long long sidx = ((long long)b * p.heads + h) * p.N + row;
+      const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
+      const float dl = row < p.N ? p.delta[sidx] : 0.f;
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t s_addr = tmem_base + lane_off + half * 64;
+        const uint32_t g_addr = tmem_base + lane_off + 128 + s * 128 + half * 64;
+        uint32_t v[32], g[32], v2[32];
+        tmem_ld_32x32(s_addr, v);
+        tmem_ld_32x32(s_addr + 32, v2);
+        tmem_ld_32x32(g_addr, g);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);            // the S buffer may be overwritten by the next tile's score MMA
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int kv_left = p.N - j * 128 - half * 64 - pass * 32;
+          if (pass == 1) {
+            tmem_ld_32x32(g_addr + 32, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v2[i];
+          }
+          if (kv_left >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              g[i] = tf32_bits_for_mma(ex2_approx(fmaf(__uint_as_float(v[i]), c, -lse2)) * (__uint_as_float(g[i]) - dl));
+          } else {                                    // ragged last tile: padded key columns contribute nothing
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float pr = (i < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[i]), c, -lse2)) : 0.f;
+              g[i] = tf32_bits_for_mma(pr * (__uint_as_float(g[i]) - dl));
+            }
+          }
+          tmem_st_32x32(g_addr + pass * 32, g);
+          tmem_st_wait();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      mbar_wait(acc_full, item_it & 1);
+      tcgen05_fence_after();
+      float* dqp = p.dqkv + ((long long)b * p.N + row) * (3ll * inner) + h * DH + half * OC;
+      {
+        uint32_t v[OC];
+        tmem_ld_cols<OC>(tmem_base + lane_off + 384 + half * OC, v);
+        tmem_ld_wait();
+        if constexpr (OC == 32) {
+          float r[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = p.round_out ? round_tf32(__uint_as_float(v[i]) * p.scale) : __uint_as_float(v[i]) * p.scale;
+          warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+        } else if (row < p.N) {
+#pragma unroll
+          for (int i = 0; i < OC; i += 4) {
+            float4 a = make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                                   __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
+            if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
+            *reinterpret_cast<float4*>(dqp + i) = a;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 // K-major (SWIZZLE_128B) view of a [B*N, ld] matrix as {ld, N, B}, box {32, rows, 1}
 static int make_kmajor_map(CUtensorMap* out, const float* ptr, long long ld, int N, int B, int box_rows) {
   const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
@@ -980,6 +1230,18 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   if (grid > p.total_items) grid = p.total_items;
   k1<<<grid, kAtcThreads, smem_kv, stream>>>(tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
+  static const bool dq128 = [] { const char* e = getenv("B200VQ_ATTN_DQ"); return e && e[0] == '1' && e[1] == '2' && e[2] == '8'; }();
+  if (dq128) {   // PROTOTYPE path, see attn_bwd_dq128_tc_kernel
+    CUtensorMap tmKM128;
+    if ((rc = make_mnmajor_map(&tmKM128, qkv, ld, N, B, 128, DH / 32))) return rc;
+    constexpr int smem_q128 = 5 * 128 * DH * 4 + kOutBoxBytes + 256 + 1024;
+    auto k3 = attn_bwd_dq128_tc_kernel<DH>;
+    static bool configured128 = false;
+    if (!configured128) { B200_CUDA_OK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q128)); configured128 = true; }
+    k3<<<grid, kAtcThreads, smem_q128, stream>>>(tmKV128, tmDO128, tmKV128, tmKM128, tmOut, p);
+    B200_LAUNCH_OK("attn_bwd_dq128_tc_kernel");
+    return 0;
+  }
   k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return 0;
