@@ -1,21 +1,20 @@
-// tcgen05 / TMEM flash-attention forward for the ViT blocks (reference layers.py:124-130).
+// tcgen05 / TMEM flash-attention forward and backward for the ViT blocks (reference layers.py:124-130).
 //
-// Two MMA-issuing warps: tcgen05.mma issue blocks while the tensor pipe executes (measured: the
-// queue is one or two instructions deep), so a single issuer serialises its own mbarrier polling
-// (~100 cycles per wait) with MMA execution.  Issuer A (warp 1) issues the score-type MMAs, issuer
-// B (warp 10) the P.V-type MMAs; cross-issuer hazards are covered by mbarriers (sfree).
-//
-// Persistent, warp-specialised, one work item = (batch, head, 128-query tile):
+// Forward.  Persistent, warp-specialised (352 threads), one work item = (batch, head, 128-query tile):
 //   warp 0      TMA producer: Q tile once per item, K and V tiles (128 keys) through 2-stage rings.
 //               q/k are K-major operands (SWIZZLE_128B, one 128-byte block per 32 head dims);
 //               V is the MN-major B operand of P.V (SWIZZLE_128B_BASE32B, 4-D tensor map).
-//   warp 1      MMA issuer: S_j = Q K_j^T (kind::tf32, 128x128 accumulator in TMEM, two S buffers),
-//               then O_j = P_j V_j with the A operand read from TMEM (P_j overwrites S_j in place).
-//               Issue order S_0 S_1 PV_0 S_2 PV_1 ... so the tensor pipe works on S_{j+1} while the
-//               softmax warps process S_j.
-//   warps 2..5  softmax: thread = query row (TMEM lane), two passes over the 128 scores of a tile
-//               (max, then exp2 + sum + tf32-rounded P written back with tcgen05.st); the running
-//               output lives in registers: o = o * alpha + (P_j V_j read back from TMEM).
+//   warp 1      MMA issuer A: S_j = Q K_j^T (kind::tf32, 128x128 accumulator in TMEM, two S buffers).
+//   warp 10     MMA issuer B: O_j = P_j V_j with the A operand read from TMEM (P_j overwrites S_j in place).
+//               Two issuing warps because tcgen05.mma issue blocks while the tensor pipe executes (measured:
+//               the queue is one or two instructions deep), so a single issuer would serialise its own mbarrier
+//               polling with MMA execution; cross-issuer hazards are covered by mbarriers (sfree).
+//   warps 2..9  softmax: a query row (TMEM lane) is shared by two threads (warps w and w+4 address the same lane
+//               quarter), each owning 64 of the tile's 128 scores and half of the output columns.  Scores stay in
+//               registers between the max and the exp2 pass; the row max is exchanged through shared memory under a
+//               64-thread named barrier; P is written back tf32-rounded with tcgen05.st; the running output lives
+//               in registers: o = o * alpha + (P_j V_j read back from TMEM), folded in while the next tile's scores
+//               are already being loaded.  Outputs leave through swizzled smem boxes + TMA stores.
 // TMEM columns: S/P buffers [0,128) [128,256), PV buffers [256,256+DH) [320,320+DH).
 #include "common.cuh"
 #include <cstdlib>

@@ -26,6 +26,34 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200vq_arch() == b"sm_100a"
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """every prototype in include/b200vq.h, parameter by parameter, against the ctypes table the host side calls
+    through (a hand-edited ABI must not drift: a missing argument would shift every later one silently)"""
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "b200vq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"([\w ]+?[\s\*])\s*(b200vq_\w+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(etb._lib.EXPORTS)
+
+    def kind_of_c(decl: str) -> str:
+        decl = decl.strip()
+        if decl in ("void", ""):
+            return ""
+        if "*" in decl:
+            return "ptr"
+        base = decl.rsplit(" ", 1)[0].strip()
+        return {"int": "int", "long long": "ll", "size_t": "size", "float": "float"}[base]
+
+    kind_of_ctypes = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll",
+                      ctypes.c_size_t: "size", ctypes.c_float: "float"}
+    for ret, name, params in protos:
+        restype, argtypes = etb._lib._SIGNATURES[name]
+        want = [k for k in (kind_of_c(p) for p in params.split(",")) if k]
+        got = [kind_of_ctypes[a] for a in argtypes]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+        assert kind_of_ctypes[restype] == ("ptr" if "*" in ret else kind_of_c(ret.strip() + " x")), name
+
+
 def test_cpu_tensors_are_rejected_loudly():
     enc = etb.ViTEncoder(image_size=32, patch_size=8, dim=64, depth=1, heads=2, mlp_dim=64)
     with pytest.raises(RuntimeError, match="no CPU path"):
