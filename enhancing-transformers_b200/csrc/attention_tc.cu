@@ -381,6 +381,294 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_FWD=otmem, DH = 64 only):
+// forward with the output kept in TMEM.  The P.V MMAs of all key tiles of an item accumulate into one O tile
+// (TMEM [256, 256+DH)); the softmax warps no longer fold P.V into registers every tile (a barrier probe + a
+// tcgen05.ld + 32 FMAs, ~700 of ~3400 cycles per tile in the trace) and rescale O only when the running max has
+// grown by more than 2^8 (lazy rescale, a few times per row at the start of an item).
+template <int DH>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attn_fwd_otmem_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
+  constexpr int KB = DH / 32;                 // 128-byte k-blocks per row
+  constexpr int TILE_BYTES = 128 * DH * 4;    // one Q / K / V tile
+  constexpr int KBLK_BYTES = 128 * 128;       // one k-block (or one MN atom of V): 128 rows x 128 B
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + TILE_BYTES;            // [2]
+  uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
+  uint8_t* obox = smem + 5 * TILE_BYTES;      // [8 softmax warps][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2]
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* o_full = bars + 14;   // [2]
+  uint64_t* o_free = bars + 16;   // the item's output has been read out of TMEM (8 softmax warps)
+  uint64_t* sfree = bars + 18;    // [2] S/P buffer consumed by the P.V MMAs (issuer B -> issuer A)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&sfree[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int T = p.kv_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
+    uint32_t kv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(Qs + kb * KBLK_BYTES, &tmQK, q_full, h * DH + kb * 32, qt * 128, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int s = kv_it & 1;
+        const uint32_t ph = (kv_it >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_3d(Ks + s * TILE_BYTES + kb * KBLK_BYTES, &tmQK, &k_full[s], inner + h * DH + kb * 32, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+          tma_load_4d(Vs + s * TILE_BYTES, &tmV, &v_full[s], 0, j * 128, (2 * inner + h * DH) / 32, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer A: S_j = Q K_j^T
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // both operands K-major
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+    const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
+    uint32_t s_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      for (int j = 0; j < T; ++j, ++s_it) {
+        const int s = s_it & 1;
+        const uint32_t ph = (s_it >> 1) & 1;
+        mbar_wait(&k_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);       // P_{j-2} (same buffer) has been consumed by issuer B
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = desc_advance(kd0, s * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + s * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
+          }
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&k_empty[s]);
+          if (j == T - 1) umma_commit<1>(q_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ------------------------------------------------------------------ MMA issuer B: O_j = P_j V_j (A operand from TMEM)
+    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // B MN-major
+    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
+    uint32_t pv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int j = 0; j < T; ++j, ++pv_it) {
+        const int s = pv_it & 1;
+        const uint32_t ph = (pv_it >> 1) & 1;
+        mbar_wait(&v_full[s], ph);
+        if (j == 0) mbar_wait(o_free, (item_it & 1) ^ 1);     // the previous item's O has been read out
+        mbar_wait(&p_full[s], ph);                             // P_j stored (and O rescaled if the row max jumped)
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
+          const uint32_t acc_on = j > 0;                       // one O accumulator per item, summed over the key tiles
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_tf32_ts(tmem_base + 256, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, acc_on | (k != 0));
+          umma_commit<1>(&o_full[s]);
+          umma_commit<1>(&v_empty[s]);
+          umma_commit<1>(&sfree[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output warps
+    // PROTOTYPE (round 2, not validated on hardware): the output accumulates in TMEM across the key tiles.
+    // A query row is shared by two threads (warps w and w+4 address the same TMEM lanes): each
+    // takes 64 of the 128 scores of a tile and half of the head dim of the output; the row max
+    // (per tile) and the row sum (once per item) are exchanged through shared memory.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      float m_run = -INFINITY, m_ref = 0.f, l = 0.f;   // true running max / reference the stored P and O are relative to
+      // the thread's 64 scores of a tile stay in registers between the max and the exp pass; those of tile
+      // j+1 are requested as soon as P_j has been handed over
+      uint32_t v0[32], v1[32];
+      mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
+      tcgen05_fence_after();
+      {
+        const uint32_t s0 = tmem_base + lane_off + (t_it & 1) * 128 + half * 64;
+        tmem_ld_32x32(s0, v0);
+        tmem_ld_32x32(s0 + 32, v1);
+      }
+      tmem_ld_wait();
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
+        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
+        if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
+            if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        float* xs = xch + (t_it & 1) * 256;
+        xs[half * 128 + row_in_tile] = mx;
+        pair_bar(q);                                        // only the two warps that share these rows
+        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
+        m_run = fmaxf(m_run, mx);
+        // Lazy rescale: P and O stay relative to m_ref until the running max has grown by more than 2^8 (both
+        // threads of a row see the same exchanged max, hence take the same decision; any reference is exact as
+        // long as P, O and the row sum share it).  tcgen05.ld/st are warp-collective: if any row of the warp
+        // needs it the whole warp rescales, rows that do not use alpha = 1.
+        bool need = false;
+        if (j == 0) m_ref = m_run;
+        else need = (m_run - m_ref) * c > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&o_full[s ^ 1], ((t_it - 1) >> 1) & 1);   // P_{j-1} V_{j-1} has landed in O; P_j V_j cannot start before p_full
+          tcgen05_fence_after();
+          const float alpha = need ? ex2_approx((m_ref - m_run) * c) : 1.f;
+          uint32_t ov[OC];
+          tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < OC; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32(tmem_base + lane_off + 256 + half * OC, ov);
+          tmem_st_wait();
+          l *= alpha;
+          if (need) m_ref = m_run;
+        }
+        const float mc = m_ref * c;
+        float sum = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
+          sum += e0; sum1 += e1;
+          v0[i] = tf32_bits_for_mma(e0);
+          v1[i] = tf32_bits_for_mma(e1);
+        }
+        l += sum + sum1;
+        tmem_st_32x32(sa, v0);
+        tmem_st_32x32(sa + 32, v1);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+        if (j + 1 < T) {
+          mbar_wait(&s_full[s ^ 1], ((t_it + 1) >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t sn = tmem_base + lane_off + (s ^ 1) * 128 + half * 64;
+          tmem_ld_32x32(sn, v0);
+          tmem_ld_32x32(sn + 32, v1);
+          tmem_ld_wait();
+        }
+      }
+      // item epilogue: O (relative to m_ref) out of TMEM, normalised by the row sum of both key halves
+      mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
+      tcgen05_fence_after();
+      float o[OC];
+      {
+        uint32_t ov[OC];
+        tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(ov[i]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      const float m = m_ref;
+      float* ls = xch + 512;
+      ls[half * 128 + row_in_tile] = l;
+      pair_bar(q);
+      l += ls[(half ^ 1) * 128 + row_in_tile];
+      const int row = qt * 128 + row_in_tile;
+      const float inv = 1.f / l;
+      if constexpr (OC == 32) {
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
+        warp_store_box(obox + (warp - 2) * 4096, &tmO, o, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+      } else if (row < p.N) {
+        float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
+#pragma unroll
+        for (int i = 0; i < OC; i += 4) {
+          float4 r = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+          if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+          *reinterpret_cast<float4*>(op + i) = r;
+        }
+      }
+      if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
+      pair_bar(q);     // ls is rewritten by the next item only after the partner has read it
+    }
+    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+
 template <int DH>
 static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, int round_out,
                               cudaStream_t stream) {
@@ -420,6 +708,17 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   auto kern = attn_fwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+  static const bool otmem = [] { const char* e = getenv("B200VQ_ATTN_FWD"); return e && e[0] == 'o'; }();
+  if constexpr (DH == 64) {
+    if (otmem) {   // PROTOTYPE path, see attn_fwd_otmem_kernel
+      auto kern2 = attn_fwd_otmem_kernel<DH>;
+      static bool configured2 = false;
+      if (!configured2) { B200_CUDA_OK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured2 = true; }
+      kern2<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, tmO, p);
+      B200_LAUNCH_OK("attn_fwd_otmem_kernel");
+      return 0;
+    }
+  }
   kern<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_tc_kernel");
   return 0;
