@@ -669,6 +669,322 @@ attn_fwd_otmem_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_con
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_FWD=2g, DH = 64 only):
+// forward with TWO softmax groups.  The per-tile work of a softmax warp is a serial chain of TMEM / mbarrier /
+// shared-memory round trips around one XU-bound exp2 pass (trace: ~300 + 220 + 160 + 300 + 1300 + 390 cycles once
+// the P.V fold is gone), so the tensor pipe and the XU idle most of the time.  Here group g (8 warps) owns the key
+// tiles j = g (mod 2): its own S/P buffer (TMEM [g*128, +128)), its own O accumulator (TMEM [256 + g*64, +64), kept
+// in TMEM with lazy rescale as in attn_fwd_otmem_kernel) and its own running (max, sum); the two partial softmaxes
+// are merged once per work item by group 0, which reads both O tiles straight out of TMEM.  The TMA producer and
+// the two MMA issuers work exactly as in the shipped kernel (S_j / P_j V_j use buffer j & 1), so while one group is
+// in its exp2 phase the other is in its latency phases.
+// 19 warps: 0 TMA, 1 issuer A, 2..9 softmax group 0, 10 issuer B, 11..18 softmax group 1.
+constexpr int kAtc2gThreads = 608;
+__device__ __forceinline__ void pair_bar_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int DH>
+__global__ void __maxnreg__(104)   // 19 warps x 104 registers fit the register file (__launch_bounds__(608) would cap at 96)
+attn_fwd_2g_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
+  static_assert(DH == 64, "two-group forward: head dim 64 only");
+  constexpr int KB = DH / 32;
+  constexpr int TILE_BYTES = 128 * DH * 4;
+  constexpr int KBLK_BYTES = 128 * 128;
+  constexpr int OC = DH / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + TILE_BYTES;            // [2]
+  uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
+  uint8_t* obox = smem + 5 * TILE_BYTES;      // [8 warps of group 0][4 KB] output store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2] = per group
+  uint64_t* p_full = bars + 12;   // [2] = per group, 8 arrivals
+  uint64_t* o_full = bars + 14;   // [2] = per group: P_j V_j committed
+  uint64_t* sfree = bars + 16;    // [2]
+  uint64_t* o_free = bars + 18;   // both O tiles of the item read out by group 0 (8 arrivals)
+  uint64_t* g1_done = bars + 19;  // group 1 has published (max, sum) of the item (8 arrivals)
+  uint64_t* g1_read = bars + 20;  // group 0 has read them (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* xch = reinterpret_cast<float*>(bars + 24);   // per group [2][2][128] tile max + [2][128] row sum = 768 floats; then g1 (m, l) [2][128]
+  float* g1_ml = xch + 2 * 768;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    mbar_init(o_free, 8); mbar_init(g1_done, 8); mbar_init(g1_read, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1); mbar_init(&sfree[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int T = p.kv_tiles;
+
+  if (warp == 0) {
+    // ---- TMA producer (as in attn_fwd_tc_kernel)
+    uint32_t kv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(Qs + kb * KBLK_BYTES, &tmQK, q_full, h * DH + kb * 32, qt * 128, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int s = kv_it & 1;
+        const uint32_t ph = (kv_it >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_3d(Ks + s * TILE_BYTES + kb * KBLK_BYTES, &tmQK, &k_full[s], inner + h * DH + kb * 32, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+          tma_load_4d(Vs + s * TILE_BYTES, &tmV, &v_full[s], 0, j * 128, (2 * inner + h * DH) / 32, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- issuer A: S_j = Q K_j^T into buffer j & 1.  NOTE: the buffer index must follow the tile parity *within the item*
+    // (group g owns tiles j = g mod 2), so items with an odd tile count restart at buffer 0: the ring counters below are
+    // per buffer, not a single running counter.
+    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);
+    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
+    const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
+    uint32_t kv_it = 0, item_it = 0;
+    uint32_t use0 = 0, use1 = 0;                   // how often S buffer 0 / 1 has been filled so far (scalars: no local-memory array)
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int st = kv_it & 1;                  // K/V smem stage: plain ring over all tiles
+        const int g = j & 1;                       // S buffer / softmax group
+        mbar_wait(&k_full[st], (kv_it >> 1) & 1);
+        const uint32_t ug = g ? use1 : use0;
+        mbar_wait(&sfree[g], (ug & 1) ^ 1);        // the group's previous P has been consumed by issuer B
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = desc_advance(kd0, st * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < DH / 8; ++k) {
+            const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
+            umma_tf32<1>(tmem_base + g * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
+          }
+          umma_commit<1>(&s_full[g]);
+          umma_commit<1>(&k_empty[st]);
+          if (j == T - 1) umma_commit<1>(q_empty);
+        }
+        __syncwarp();
+        if (g) ++use1; else ++use0;
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: O_g += P_j V_j (A from TMEM), one accumulator per group and item
+    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);
+    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
+    uint32_t kv_it = 0, item_it = 0;
+    uint32_t use0 = 0, use1 = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int st = kv_it & 1;
+        const int g = j & 1;
+        mbar_wait(&v_full[st], (kv_it >> 1) & 1);
+        if (j == 0) mbar_wait(o_free, (item_it & 1) ^ 1);        // previous item's O tiles have been read out
+        const uint32_t ug = g ? use1 : use0;
+        mbar_wait(&p_full[g], ug & 1);                           // P_j stored (and O_g rescaled if needed)
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = desc_advance(vd0, st * TILE_BYTES);
+          const uint32_t acc_on = j >= 2;                        // first tile of each group starts its accumulator
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_tf32_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, acc_on | (k != 0));
+          umma_commit<1>(&o_full[g]);
+          umma_commit<1>(&v_empty[st]);
+          umma_commit<1>(&sfree[g]);
+        }
+        __syncwarp();
+        if (g) ++use1; else ++use0;
+      }
+    }
+  } else {
+    // ---- softmax groups
+    const int g = warp > kIssuerB ? 1 : 0;
+    const int gw = g ? warp - 11 : warp - 2;            // 0..7 inside the group
+    const int q = warp & 3;                             // TMEM lane quarter this warp may touch
+    // the two warps of a group that share lane quarter q: group 0 -> warps q' and q'+4 of 2..9, group 1 -> of 11..18.
+    // Which of the two this warp is (column half 0 / 1) = whether it is the first or second warp with this (warp & 3).
+    const int first_with_q = g ? 11 + ((q - 3) & 3) : 2 + ((q - 2) & 3);
+    const int hf = warp == first_with_q ? 0 : 1;
+    const int bar_id = 2 + g * 4 + q;                   // named barriers 2..9 (64 threads each)
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const float c = p.scale * kLog2eF;
+    float* gx = xch + g * 768;                          // this group's exchange area
+    uint32_t use = 0;                                   // tiles this group has processed so far (ring phase of its barriers)
+    uint32_t item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      float m_run = -INFINITY, m_ref = 0.f, l = 0.f;
+      int jl = 0;                                       // tiles of this item done by this group
+      for (int j = g; j < T; j += 2, ++use, ++jl) {
+        mbar_wait(&s_full[g], use & 1);
+        tcgen05_fence_after();
+        const uint32_t sa = tmem_base + lane_off + g * 128 + hf * 64;
+        const int kv_left = p.N - j * 128 - hf * 64;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(sa, v0);
+        tmem_ld_32x32(sa + 32, v1);
+        tmem_ld_wait();
+        if (kv_left < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_left) v0[i] = 0xff800000u;
+            if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        float* xs = gx + (use & 1) * 256;
+        xs[hf * 128 + row_in_tile] = mx;
+        pair_bar_id(bar_id);
+        mx = fmaxf(mx, xs[(hf ^ 1) * 128 + row_in_tile]);
+        m_run = fmaxf(m_run, mx);
+        bool need = false;
+        if (jl == 0) m_ref = m_run;
+        else need = (m_run - m_ref) * c > 8.f;
+        if (__any_sync(0xffffffffu, need)) {            // lazy rescale of O_g (see attn_fwd_otmem_kernel)
+          mbar_wait(&o_full[g], (use - 1) & 1);         // this group's previous P.V has landed
+          tcgen05_fence_after();
+          const float alpha = need ? ex2_approx((m_ref - m_run) * c) : 1.f;
+          uint32_t ov[OC];
+          tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64 + hf * OC, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < OC; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32(tmem_base + lane_off + 256 + g * 64 + hf * OC, ov);
+          tmem_st_wait();
+          l *= alpha;
+          if (need) m_ref = m_run;
+        }
+        const float mc = m_ref * c;
+        float sum = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
+          sum += e0; sum1 += e1;
+          v0[i] = tf32_bits_for_mma(e0);
+          v1[i] = tf32_bits_for_mma(e1);
+        }
+        l += sum + sum1;
+        tmem_st_32x32(sa, v0);
+        tmem_st_32x32(sa + 32, v1);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+      // ---- end of item: row sum of the group (both column halves), then the merge by group 0
+      float* ls = gx + 512;
+      ls[hf * 128 + row_in_tile] = l;
+      pair_bar_id(bar_id);
+      l += ls[(hf ^ 1) * 128 + row_in_tile];
+      if (g == 1) {
+        mbar_wait(g1_read, (item_it & 1) ^ 1);          // group 0 has consumed the previous item's values
+        if (hf == 0) {
+          g1_ml[row_in_tile] = jl > 0 ? m_ref : -INFINITY;
+          g1_ml[128 + row_in_tile] = jl > 0 ? l : 0.f;
+        }
+        pair_bar_id(bar_id);                            // ls free for the next item; the hf==0 stores are ordered before the arrive
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g1_done);
+      } else {
+        // group 0 always has >= 1 tile (T >= 1)
+        mbar_wait(&o_full[0], (use - 1) & 1);
+        if (T > 1) {
+          // group 1's last tile of this item: its o_full phase counter equals the number of tiles it has done in total
+          mbar_wait(g1_done, item_it & 1);
+        }
+        tcgen05_fence_after();
+        float mB = -INFINITY, lB = 0.f;
+        if (T > 1) { mB = g1_ml[row_in_tile]; lB = g1_ml[128 + row_in_tile]; }
+        const float m_f = fmaxf(m_ref, mB);
+        const float wA = ex2_approx((m_ref - m_f) * c);
+        const float wB = T > 1 ? ex2_approx((mB - m_f) * c) : 0.f;
+        const float l_f = l * wA + lB * wB;
+        float o[OC];
+        {
+          uint32_t oa[OC];
+          tmem_ld_32x32(tmem_base + lane_off + 256 + hf * OC, oa);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(oa[i]) * wA;
+        }
+        if (T > 1) {
+          // group 1's P.V of its last tile: issuer B commits o_full[1] after it; wait for that commit here
+          // (group 0 does not otherwise track o_full[1]'s phase: it is the number of group-1 tiles so far, minus one)
+          const uint32_t g1_tiles_before = item_it * (uint32_t)(T / 2);           // tiles group 1 did in earlier items of THIS CTA
+          mbar_wait(&o_full[1], (g1_tiles_before + (uint32_t)(T / 2) - 1) & 1);
+          tcgen05_fence_after();
+          uint32_t ob[OC];
+          tmem_ld_32x32(tmem_base + lane_off + 256 + 64 + hf * OC, ob);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < OC; ++i) o[i] = fmaf(__uint_as_float(ob[i]), wB, o[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(o_free); mbar_arrive(g1_read); }
+        const int row = qt * 128 + row_in_tile;
+        const float inv = 1.f / l_f;
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
+        warp_store_box(obox + gw * 4096, &tmO, o, h * DH + hf * OC, qt * 128 + q * 32, b, lane);
+        if (row < p.N && hf == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m_f * p.scale + logf(l_f);
+        pair_bar_id(bar_id);                            // ls is rewritten by the next item only after the partner has read it
+      }
+    }
+    if (g == 0 && lane == 0) bulk_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 template <int DH>
 static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, int round_out,
                               cudaStream_t stream) {
@@ -709,7 +1025,17 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
   static bool configured = false;
   if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
   static const bool otmem = [] { const char* e = getenv("B200VQ_ATTN_FWD"); return e && e[0] == 'o'; }();
+  static const bool twog = [] { const char* e = getenv("B200VQ_ATTN_FWD"); return e && e[0] == '2'; }();
   if constexpr (DH == 64) {
+    if (twog) {   // PROTOTYPE path, see attn_fwd_2g_kernel
+      constexpr int smem2 = 5 * 128 * DH * 4 + kOutBoxBytes + 256 + (2 * 768 + 256) * 4 + 1024;
+      auto kern3 = attn_fwd_2g_kernel<DH>;
+      static bool configured3 = false;
+      if (!configured3) { B200_CUDA_OK(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2)); configured3 = true; }
+      kern3<<<grid, kAtc2gThreads, smem2, stream>>>(tmQK, tmV, tmO, p);
+      B200_LAUNCH_OK("attn_fwd_2g_kernel");
+      return 0;
+    }
     if (otmem) {   // PROTOTYPE path, see attn_fwd_otmem_kernel
       auto kern2 = attn_fwd_otmem_kernel<DH>;
       static bool configured2 = false;
