@@ -60,7 +60,7 @@ def lib() -> ctypes.CDLL:
                     raise RuntimeError(
                         f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
                         "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
-                        "`make -C enhancing-transformers_b200/csrc`.")
+                        "`make -C enhancing_transformers_b200/csrc`.")
                 handle = ctypes.CDLL(LIB_PATH)
                 for name, (res, args) in _SIGNATURES.items():
                     fn = getattr(handle, name)      # AttributeError here == header/.so mismatch

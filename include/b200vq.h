@@ -3,7 +3,7 @@
  *
  * Boundary.  The reference has no FFI of its own on this path: its
  * ViTEncoder / ViTDecoder / VectorQuantizer are nn.Modules whose arithmetic lives in ATen.  The
- * drop-in boundary is therefore the nn.Module surface (enhancing-transformers_b200/layers.py,
+ * drop-in boundary is therefore the nn.Module surface (enhancing_transformers_b200/layers.py,
  * quantizers.py) and *this* header is what those modules bind with ctypes -- each entry point
  * names the reference line(s) whose ATen calls it replaces.
  *

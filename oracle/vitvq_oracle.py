@@ -7,7 +7,7 @@ reference's ``enhancing/modules/stage1/layers.py`` (ViTEncoder / ViTDecoder) and
 (``vitvqgan.py:38-39,63,69``).  It exists so that ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs have something to check the CUDA path
 against on a machine where ``/root/reference`` does not exist.  Nothing under the product
-package (``enhancing-transformers_b200/``) may import it.
+package (``enhancing_transformers_b200/``) may import it.
 
 Parity pin: the reference ships no tests and no golden vectors, so this
 oracle is pinned against outputs of the *reference itself*, generated in the build container by
