@@ -18,24 +18,35 @@ _SIGNATURES = {
     "b200vq_last_error": (ctypes.c_char_p, []),
     "b200vq_arch": (ctypes.c_char_p, []),
     "b200vq_launch_count": (c_ll, []),
+    "b200vq_set_sm_limit": (c_i, [c_i]),
     "b200vq_gemm_tf32": (c_i, [c_f, c_ll, c_i, c_f, c_ll, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_ll, c_f, c_f, c_ll, c_i,
                                c_f, c_ll, c_f, c_i, c_i, c_i, c_i, c_f]),
-    "b200vq_splitk_reduce": (c_i, [c_f, c_i, c_ll, c_ll, c_f, c_f]),
-    "b200vq_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
+    "b200vq_gemm_3xtf32": (c_i, [c_f, c_f, c_ll, c_i, c_f, c_f, c_ll, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_ll, c_f, c_f, c_ll,
+                                 c_i, c_f, c_ll, c_f, c_i, c_i, c_i, c_f]),
+    "b200vq_gemm_f16": (c_i, [c_f, c_ll, c_i, c_f, c_ll, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_ll, c_f, c_f, c_ll, c_i,
+                              c_f, c_ll, c_f, c_i, c_i, c_f, c_i, c_i, c_f]),
+    "b200vq_splitk_reduce": (c_i, [c_f, c_i, c_ll, c_ll, c_f, c_f, c_f]),
+    "b200vq_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "b200vq_layernorm_bwd_workspace_bytes": (c_sz, [c_i]),
-    "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
-    "b200vq_attention_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
-    "b200vq_attention_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
+    "b200vq_attention_fwd": (c_i, [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "b200vq_attention_bwd": (c_i, [c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "b200vq_attention_exact_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "b200vq_attention_exact_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "b200vq_vq_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
-    "b200vq_vq_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f]),
-    "b200vq_vq_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
-    "b200vq_vq_embed": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f]),
+    "b200vq_vq_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f, c_sz, c_f]),
+    "b200vq_vq_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "b200vq_vq_embed": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "b200vq_patchify": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
     "b200vq_unpatchify": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f]),
     "b200vq_colsum_workspace_bytes": (c_sz, [c_i]),
     "b200vq_colsum": (c_i, [c_f, c_ll, c_i, c_i, c_f, c_f, c_sz, c_f]),
     "b200vq_round_tf32": (c_i, [c_f, c_f, c_ll, c_f]),
     "b200vq_add_rows_mod": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_f]),
+    "b200vq_split_tf32_lo": (c_i, [c_f, c_f, c_ll, c_f]),
+    "b200vq_to_half": (c_i, [c_f, c_f, c_ll, c_f, c_f]),
+    "b200vq_grad_scale_workspace_bytes": (c_sz, []),
+    "b200vq_grad_scale": (c_i, [c_f, c_ll, c_i, c_f, c_f, c_sz, c_f]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

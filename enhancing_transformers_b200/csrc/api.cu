@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -23,38 +24,71 @@ int set_error(int code, const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static PerDevice cache;
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (!cache.done[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache.value[dev] = n;
+    cache.done[dev] = true;
   }
-  return n;
+  return cache.value[dev];
+}
+
+static std::atomic<int> g_sm_limit{-1};
+int sm_limit() {
+  int v = g_sm_limit.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("B200VQ_SM_LIMIT");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    g_sm_limit.store(v);
+  }
+  return v;
 }
 
 // implemented in the other translation units
 int gemm_tf32(const float*, long long, int, const float*, long long, int, float*, long long, int, int, int, int, long long,
               const float*, const float*, long long, int, const float*, long long, float*, int, int, int, int, cudaStream_t);
-int splitk_reduce(const float*, int, long long, long long, float*, cudaStream_t);
-int layernorm_forward(const float*, const float*, const float*, float*, float*, float*, int, int, int, cudaStream_t);
+int gemm_3xtf32(const float*, const float*, long long, int, const float*, const float*, long long, int, float*, long long, int, int,
+                int, int, long long, const float*, const float*, long long, int, const float*, long long, float*, int, int, int,
+                cudaStream_t);
+int gemm_f16(const void*, long long, int, const void*, long long, int, void*, long long, int, int, int, int, int, long long,
+             const float*, const float*, long long, int, const void*, long long, float*, int, int, const float*, int, int,
+             cudaStream_t);
+int splitk_reduce(const float*, int, long long, long long, const float*, float*, cudaStream_t);
+int layernorm_forward(const float*, const float*, const float*, float*, void*, float*, float*, int, int, int, cudaStream_t);
 size_t layernorm_bwd_workspace_bytes(int);
-int layernorm_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*,
-                       float*, float*, int, int, int, void*, size_t, cudaStream_t);
-int attention_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
-int attention_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float, int,
-                       cudaStream_t);
+int layernorm_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*, void*,
+                       const float*, float*, float*, float*, int, int, int, void*, size_t, cudaStream_t);
+int attention_forward(const float*, void*, int, float*, int, int, int, int, float, int, cudaStream_t);
+int attention_backward(const float*, const void*, int, const float*, const float*, void*, int, const float*, float*, int, int,
+                       int, int, float, int, cudaStream_t);
+int attention_exact_forward(const float*, float*, float*, int, int, int, int, float, cudaStream_t);
+int attention_exact_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float,
+                             cudaStream_t);
 size_t vq_workspace_bytes(int, int, int);
-int vq_forward(const float*, const float*, float*, long long*, float*, int, int, int, int, float, void*, size_t, cudaStream_t);
+int vq_forward(const float*, const float*, float*, long long*, float*, int, int, int, int, float, int, void*, size_t, cudaStream_t);
 int vq_backward(const float*, const float*, const long long*, const float*, const float*, float*, float*, int, int, int, int,
-                int, float, cudaStream_t);
-int vq_embed(const float*, const long long*, float*, int, int, int, int, cudaStream_t);
+                int, float, int, cudaStream_t);
+int vq_embed(const float*, const long long*, float*, int, int, int, int, int, cudaStream_t);
 int patchify(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int unpatchify(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 size_t colsum_workspace_bytes(int);
 int colsum(const float*, long long, int, int, float*, void*, size_t, cudaStream_t);
 int round_tf32_copy(const float*, float*, long long, cudaStream_t);
 int add_rows_mod(const float*, const float*, float*, long long, int, int, cudaStream_t);
+int split_tf32_lo(const float*, float*, long long, cudaStream_t);
+int to_half(const float*, void*, long long, const float*, cudaStream_t);
+size_t grad_scale_workspace_bytes();
+int grad_scale(const float*, long long, int, float*, void*, size_t, cudaStream_t);
 
 }  // namespace b200
 
@@ -68,6 +102,8 @@ const char* b200vq_last_error(void) { return g_err; }
 const char* b200vq_arch(void) { return "sm_100a"; }
 long long b200vq_launch_count(void) { return g_launches.load(); }
 
+int b200vq_set_sm_limit(int n) { g_sm_limit.store(n < 0 ? 0 : n); return 0; }
+
 int b200vq_gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major, float* C,
                      long long ldc, int M, int N, int K, int splits, long long c_split_stride, const float* bias,
                      const float* res, long long ldres, int res_row_mod, const float* aux, long long ldaux,
@@ -75,39 +111,65 @@ int b200vq_gemm_tf32(const float* A, long long lda, int a_major, const float* B,
   return gemm_tf32(A, lda, a_major, B, ldb, b_major, C, ldc, M, N, K, splits, c_split_stride, bias, res, ldres, res_row_mod,
                    aux, ldaux, colsum_part, act, round_out, cta_group, bn, S(stream));
 }
-int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, void* stream) {
-  return splitk_reduce(part, splits, n, split_stride, out, S(stream));
+int b200vq_gemm_3xtf32(const float* A, const float* A_lo, long long lda, int a_major, const float* B, const float* B_lo,
+                       long long ldb, int b_major, float* C, long long ldc, int M, int N, int K, int splits,
+                       long long c_split_stride, const float* bias, const float* res, long long ldres, int res_row_mod,
+                       const float* aux, long long ldaux, float* colsum_part, int act, int cta_group, int bn, void* stream) {
+  return gemm_3xtf32(A, A_lo, lda, a_major, B, B_lo, ldb, b_major, C, ldc, M, N, K, splits, c_split_stride, bias, res, ldres,
+                     res_row_mod, aux, ldaux, colsum_part, act, cta_group, bn, S(stream));
 }
-int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M,
-                         int D, int round_out, void* stream) {
-  return layernorm_forward(x, gamma, beta, y, mean, rstd, M, D, round_out, S(stream));
+int b200vq_gemm_f16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* C, long long ldc,
+                    int out_half, int M, int N, int K, int splits, long long c_split_stride, const float* bias,
+                    const float* res, long long ldres, int res_row_mod, const void* aux, long long ldaux, float* colsum_part,
+                    int act, int round_out, const float* alpha, int cta_group, int bn, void* stream) {
+  return gemm_f16(A, lda, a_major, B, ldb, b_major, C, ldc, out_half, M, N, K, splits, c_split_stride, bias, res, ldres,
+                  res_row_mod, aux, ldaux, colsum_part, act, round_out, alpha, cta_group, bn, S(stream));
+}
+int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, const float* alpha, float* out,
+                         void* stream) {
+  return splitk_reduce(part, splits, n, split_stride, alpha, out, S(stream));
+}
+int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y16, float* mean, float* rstd,
+                         int M, int D, int round_out, void* stream) {
+  return layernorm_forward(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, S(stream));
 }
 size_t b200vq_layernorm_bwd_workspace_bytes(int D) { return layernorm_bwd_workspace_bytes(D); }
 int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
-                         int round_out, void* workspace, size_t ws_bytes, void* stream) {
-  return layernorm_backward(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, dxsum, M, D, round_out, workspace, ws_bytes,
-                            S(stream));
+                         const float* dres, float* dx, void* dx16, const float* dx16_scale, float* dgamma, float* dbeta,
+                         float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes, void* stream) {
+  return layernorm_backward(dy, x, mean, rstd, gamma, dres, dx, dx16, dx16_scale, dgamma, dbeta, dxsum, M, D, round_out,
+                            workspace, ws_bytes, S(stream));
 }
-int b200vq_attention_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
+int b200vq_attention_fwd(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, int dh, float scale,
                          int round_out, void* stream) {
-  return attention_forward(qkv, out, lse, B, N, heads, dh, scale, round_out, S(stream));
+  return attention_forward(qkv, out, out_half, lse, B, N, heads, dh, scale, round_out, S(stream));
 }
-int b200vq_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv, float* delta,
-                         int B, int N, int heads, int dh, float scale, int round_out, void* stream) {
-  return attention_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, round_out, S(stream));
+int b200vq_attention_bwd(const float* qkv, const void* out, int out_half, const float* lse, const float* dout, void* dqkv,
+                         int dqkv_half, const float* dqkv_scale, float* delta, int B, int N, int heads, int dh, float scale,
+                         int round_out, void* stream) {
+  return attention_backward(qkv, out, out_half, lse, dout, dqkv, dqkv_half, dqkv_scale, delta, B, N, heads, dh, scale,
+                            round_out, S(stream));
+}
+int b200vq_attention_exact_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
+                               void* stream) {
+  return attention_exact_forward(qkv, out, lse, B, N, heads, dh, scale, S(stream));
+}
+int b200vq_attention_exact_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                               float* delta, int B, int N, int heads, int dh, float scale, void* stream) {
+  return attention_exact_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, S(stream));
 }
 size_t b200vq_vq_workspace_bytes(int M, int K, int depth) { return vq_workspace_bytes(M, K, depth); }
 int b200vq_vq_fwd(const float* z, const float* E, float* out, long long* idx, float* loss, int M, int K, int D, int depth,
-                  float beta, void* workspace, size_t ws_bytes, void* stream) {
-  return vq_forward(z, E, out, idx, loss, M, K, D, depth, beta, workspace, ws_bytes, S(stream));
+                  float beta, int use_norm, void* workspace, size_t ws_bytes, void* stream) {
+  return vq_forward(z, E, out, idx, loss, M, K, D, depth, beta, use_norm, workspace, ws_bytes, S(stream));
 }
 int b200vq_vq_bwd(const float* z, const float* E, const long long* idx, const float* g_out, const float* g_loss, float* gz,
-                  float* gE, int M, int K, int D, int depth, int residual, float beta, void* stream) {
-  return vq_backward(z, E, idx, g_out, g_loss, gz, gE, M, K, D, depth, residual, beta, S(stream));
+                  float* gE, int M, int K, int D, int depth, int residual, float beta, int use_norm, void* stream) {
+  return vq_backward(z, E, idx, g_out, g_loss, gz, gE, M, K, D, depth, residual, beta, use_norm, S(stream));
 }
-int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, int K, int D, int depth, void* stream) {
-  return vq_embed(E, codes, out, M, K, D, depth, S(stream));
+int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, int K, int D, int depth, int use_norm,
+                    void* stream) {
+  return vq_embed(E, codes, out, M, K, D, depth, use_norm, S(stream));
 }
 int b200vq_patchify(const float* img, float* patches, int B, int C, int H, int W, int p, int round_out, void* stream) {
   return patchify(img, patches, B, C, H, W, p, round_out, S(stream));
@@ -123,6 +185,16 @@ int b200vq_round_tf32(const float* in, float* out, long long n, void* stream) { 
 
 int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream) {
   return add_rows_mod(x, table, out, M, D, R, S(stream));
+}
+
+int b200vq_split_tf32_lo(const float* in, float* lo, long long n, void* stream) { return split_tf32_lo(in, lo, n, S(stream)); }
+int b200vq_to_half(const float* in, void* out, long long n, const float* scale, void* stream) {
+  return to_half(in, out, n, scale, S(stream));
+}
+size_t b200vq_grad_scale_workspace_bytes(void) { return grad_scale_workspace_bytes(); }
+int b200vq_grad_scale(const float* g, long long n, int target_log2, float* scale2, void* workspace, size_t ws_bytes,
+                      void* stream) {
+  return grad_scale(g, n, target_log2, scale2, workspace, ws_bytes, S(stream));
 }
 
 }  // extern "C"

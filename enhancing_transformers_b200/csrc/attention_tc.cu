@@ -87,8 +87,33 @@ __device__ __forceinline__ void warp_store_box(uint8_t* box, const CUtensorMap* 
   }
 }
 
+// fp16 flavour: the same 32 x 32 values, multiplied by `mul`, leave as a 32-row x 64-byte box (saturating
+// fp16; un-swizzled -- this runs once per work item, the bank conflicts of the 16-byte row stores are noise).
+__device__ __forceinline__ void warp_store_box_h(uint8_t* box, const CUtensorMap* tm, const float (&r)[32], float mul, int c0, int c1,
+                                                 int c2, int lane) {
+  if (lane == 0) bulk_wait_group_read<0>();
+  __syncwarp();
+  uint8_t* rowp = box + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    pk.x = pack_half2_sat(r[8 * j] * mul, r[8 * j + 1] * mul);
+    pk.y = pack_half2_sat(r[8 * j + 2] * mul, r[8 * j + 3] * mul);
+    pk.z = pack_half2_sat(r[8 * j + 4] * mul, r[8 * j + 5] * mul);
+    pk.w = pack_half2_sat(r[8 * j + 6] * mul, r[8 * j + 7] * mul);
+    *reinterpret_cast<uint4*>(rowp + j * 16) = pk;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, box, c0, c1, c2);
+    bulk_commit_group();
+  }
+}
+
 struct AttnTcParams {
-  float* out;        // [B*N, heads*DH]
+  float* out;        // [B*N, heads*DH] fp32, or fp16 when out_half
+  int out_half;      // 1: the output feeds an fp16 GEMM (to_out): store fp16
   float* lse;        // [B*heads*N]
   int B, N, heads;
   int q_tiles, kv_tiles, total_items;
@@ -353,9 +378,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       const int row = qt * 128 + row_in_tile;
       const float inv = 1.f / l;
       if constexpr (OC == 32) {
+        if (p.out_half) {
+          warp_store_box_h(obox + (warp - 2) * 4096, &tmO, o, inv, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+        } else {
 #pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
-        warp_store_box(obox + (warp - 2) * 4096, &tmO, o, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+          for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
+          warp_store_box(obox + (warp - 2) * 4096, &tmO, o, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+        }
+      } else if (row < p.N && p.out_half) {
+        __half* op = reinterpret_cast<__half*>(p.out) + ((long long)b * p.N + row) * inner + h * DH + half * OC;
+#pragma unroll
+        for (int i = 0; i < OC; i += 8) {
+          uint4 pk;
+          pk.x = pack_half2_sat(o[i] * inv, o[i + 1] * inv); pk.y = pack_half2_sat(o[i + 2] * inv, o[i + 3] * inv);
+          pk.z = pack_half2_sat(o[i + 4] * inv, o[i + 5] * inv); pk.w = pack_half2_sat(o[i + 6] * inv, o[i + 7] * inv);
+          *reinterpret_cast<uint4*>(op + i) = pk;
+        }
       } else if (row < p.N) {
         float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
 #pragma unroll
@@ -380,613 +418,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_FWD=otmem, DH = 64 only):
-// forward with the output kept in TMEM.  The P.V MMAs of all key tiles of an item accumulate into one O tile
-// (TMEM [256, 256+DH)); the softmax warps no longer fold P.V into registers every tile (a barrier probe + a
-// tcgen05.ld + 32 FMAs, ~700 of ~3400 cycles per tile in the trace) and rescale O only when the running max has
-// grown by more than 2^8 (lazy rescale, a few times per row at the start of an item).
 template <int DH>
-__global__ void __launch_bounds__(kAtcThreads, 1)
-attn_fwd_otmem_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
-  constexpr int KB = DH / 32;                 // 128-byte k-blocks per row
-  constexpr int TILE_BYTES = 128 * DH * 4;    // one Q / K / V tile
-  constexpr int KBLK_BYTES = 128 * 128;       // one k-block (or one MN atom of V): 128 rows x 128 B
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ks = smem + TILE_BYTES;            // [2]
-  uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
-  uint8_t* obox = smem + 5 * TILE_BYTES;      // [8 softmax warps][4 KB] output store boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* s_full = bars + 10;   // [2]
-  uint64_t* p_full = bars + 12;   // [2]
-  uint64_t* o_full = bars + 14;   // [2]
-  uint64_t* o_free = bars + 16;   // the item's output has been read out of TMEM (8 softmax warps)
-  uint64_t* sfree = bars + 18;    // [2] S/P buffer consumed by the P.V MMAs (issuer B -> issuer A)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    mbar_init(o_free, 8);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&sfree[s], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int inner = p.heads * DH;
-  const int T = p.kv_tiles;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
-    uint32_t kv_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      const int qt = w % p.q_tiles;
-      const int bh = w / p.q_tiles;
-      const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(q_empty, (item_it & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, TILE_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) tma_load_3d(Qs + kb * KBLK_BYTES, &tmQK, q_full, h * DH + kb * 32, qt * 128, b);
-      }
-      __syncwarp();
-      for (int j = 0; j < T; ++j, ++kv_it) {
-        const int s = kv_it & 1;
-        const uint32_t ph = (kv_it >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-#pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(Ks + s * TILE_BYTES + kb * KBLK_BYTES, &tmQK, &k_full[s], inner + h * DH + kb * 32, j * 128, b);
-        }
-        __syncwarp();
-        mbar_wait(&v_empty[s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-          tma_load_4d(Vs + s * TILE_BYTES, &tmV, &v_full[s], 0, j * 128, (2 * inner + h * DH) / 32, b);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer A: S_j = Q K_j^T
-    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);   // both operands K-major
-    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
-    const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
-    uint32_t s_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(q_full, item_it & 1);
-      for (int j = 0; j < T; ++j, ++s_it) {
-        const int s = s_it & 1;
-        const uint32_t ph = (s_it >> 1) & 1;
-        mbar_wait(&k_full[s], ph);
-        mbar_wait(&sfree[s], ph ^ 1);       // P_{j-2} (same buffer) has been consumed by issuer B
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t kd = desc_advance(kd0, s * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < DH / 8; ++k) {
-            const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
-            umma_tf32<1>(tmem_base + s * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
-          }
-          umma_commit<1>(&s_full[s]);
-          umma_commit<1>(&k_empty[s]);
-          if (j == T - 1) umma_commit<1>(q_empty);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == kIssuerB) {
-    // ------------------------------------------------------------------ MMA issuer B: O_j = P_j V_j (A operand from TMEM)
-    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);    // B MN-major
-    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
-    uint32_t pv_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      for (int j = 0; j < T; ++j, ++pv_it) {
-        const int s = pv_it & 1;
-        const uint32_t ph = (pv_it >> 1) & 1;
-        mbar_wait(&v_full[s], ph);
-        if (j == 0) mbar_wait(o_free, (item_it & 1) ^ 1);     // the previous item's O has been read out
-        mbar_wait(&p_full[s], ph);                             // P_j stored (and O rescaled if the row max jumped)
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t vd = desc_advance(vd0, s * TILE_BYTES);
-          const uint32_t acc_on = j > 0;                       // one O accumulator per item, summed over the key tiles
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_tf32_ts(tmem_base + 256, tmem_base + s * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, acc_on | (k != 0));
-          umma_commit<1>(&o_full[s]);
-          umma_commit<1>(&v_empty[s]);
-          umma_commit<1>(&sfree[s]);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax / output warps
-    // PROTOTYPE (round 2, not validated on hardware): the output accumulates in TMEM across the key tiles.
-    // A query row is shared by two threads (warps w and w+4 address the same TMEM lanes): each
-    // takes 64 of the 128 scores of a tile and half of the head dim of the output; the row max
-    // (per tile) and the row sum (once per item) are exchanged through shared memory.
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int OC = DH / 2;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const int row_in_tile = q * 32 + lane;
-    const float c = p.scale * kLog2eF;
-    uint32_t t_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-      const int qt = w % p.q_tiles;
-      const int bh = w / p.q_tiles;
-      const int h = bh % p.heads, b = bh / p.heads;
-      float m_run = -INFINITY, m_ref = 0.f, l = 0.f;   // true running max / reference the stored P and O are relative to
-      // the thread's 64 scores of a tile stay in registers between the max and the exp pass; those of tile
-      // j+1 are requested as soon as P_j has been handed over
-      uint32_t v0[32], v1[32];
-      mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
-      tcgen05_fence_after();
-      {
-        const uint32_t s0 = tmem_base + lane_off + (t_it & 1) * 128 + half * 64;
-        tmem_ld_32x32(s0, v0);
-        tmem_ld_32x32(s0 + 32, v1);
-      }
-      tmem_ld_wait();
-      for (int j = 0; j < T; ++j, ++t_it) {
-        const int s = t_it & 1;
-        const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
-        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
-        if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
-            if (32 + i >= kv_left) v1[i] = 0xff800000u;
-          }
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        float* xs = xch + (t_it & 1) * 256;
-        xs[half * 128 + row_in_tile] = mx;
-        pair_bar(q);                                        // only the two warps that share these rows
-        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
-        m_run = fmaxf(m_run, mx);
-        // Lazy rescale: P and O stay relative to m_ref until the running max has grown by more than 2^8 (both
-        // threads of a row see the same exchanged max, hence take the same decision; any reference is exact as
-        // long as P, O and the row sum share it).  tcgen05.ld/st are warp-collective: if any row of the warp
-        // needs it the whole warp rescales, rows that do not use alpha = 1.
-        bool need = false;
-        if (j == 0) m_ref = m_run;
-        else need = (m_run - m_ref) * c > 8.f;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(&o_full[s ^ 1], ((t_it - 1) >> 1) & 1);   // P_{j-1} V_{j-1} has landed in O; P_j V_j cannot start before p_full
-          tcgen05_fence_after();
-          const float alpha = need ? ex2_approx((m_ref - m_run) * c) : 1.f;
-          uint32_t ov[OC];
-          tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, ov);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < OC; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st_32x32(tmem_base + lane_off + 256 + half * OC, ov);
-          tmem_st_wait();
-          l *= alpha;
-          if (need) m_ref = m_run;
-        }
-        const float mc = m_ref * c;
-        float sum = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
-          sum += e0; sum1 += e1;
-          v0[i] = tf32_bits_for_mma(e0);
-          v1[i] = tf32_bits_for_mma(e1);
-        }
-        l += sum + sum1;
-        tmem_st_32x32(sa, v0);
-        tmem_st_32x32(sa + 32, v1);
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
-        if (j + 1 < T) {
-          mbar_wait(&s_full[s ^ 1], ((t_it + 1) >> 1) & 1);
-          tcgen05_fence_after();
-          const uint32_t sn = tmem_base + lane_off + (s ^ 1) * 128 + half * 64;
-          tmem_ld_32x32(sn, v0);
-          tmem_ld_32x32(sn + 32, v1);
-          tmem_ld_wait();
-        }
-      }
-      // item epilogue: O (relative to m_ref) out of TMEM, normalised by the row sum of both key halves
-      mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
-      tcgen05_fence_after();
-      float o[OC];
-      {
-        uint32_t ov[OC];
-        tmem_ld_cols<OC>(tmem_base + lane_off + 256 + half * OC, ov);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(ov[i]);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      const float m = m_ref;
-      float* ls = xch + 512;
-      ls[half * 128 + row_in_tile] = l;
-      pair_bar(q);
-      l += ls[(half ^ 1) * 128 + row_in_tile];
-      const int row = qt * 128 + row_in_tile;
-      const float inv = 1.f / l;
-      if constexpr (OC == 32) {
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
-        warp_store_box(obox + (warp - 2) * 4096, &tmO, o, h * DH + half * OC, qt * 128 + q * 32, b, lane);
-      } else if (row < p.N) {
-        float* op = p.out + ((long long)b * p.N + row) * inner + h * DH + half * OC;
-#pragma unroll
-        for (int i = 0; i < OC; i += 4) {
-          float4 r = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
-          if (p.round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-          *reinterpret_cast<float4*>(op + i) = r;
-        }
-      }
-      if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
-      pair_bar(q);     // ls is rewritten by the next item only after the partner has read it
-    }
-    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_FWD=2g, DH = 64 only):
-// forward with TWO softmax groups.  The per-tile work of a softmax warp is a serial chain of TMEM / mbarrier /
-// shared-memory round trips around one XU-bound exp2 pass (trace: ~300 + 220 + 160 + 300 + 1300 + 390 cycles once
-// the P.V fold is gone), so the tensor pipe and the XU idle most of the time.  Here group g (8 warps) owns the key
-// tiles j = g (mod 2): its own S/P buffer (TMEM [g*128, +128)), its own O accumulator (TMEM [256 + g*64, +64), kept
-// in TMEM with lazy rescale as in attn_fwd_otmem_kernel) and its own running (max, sum); the two partial softmaxes
-// are merged once per work item by group 0, which reads both O tiles straight out of TMEM.  The TMA producer and
-// the two MMA issuers work exactly as in the shipped kernel (S_j / P_j V_j use buffer j & 1), so while one group is
-// in its exp2 phase the other is in its latency phases.
-// 19 warps: 0 TMA, 1 issuer A, 2..9 softmax group 0, 10 issuer B, 11..18 softmax group 1.
-constexpr int kAtc2gThreads = 608;
-__device__ __forceinline__ void pair_bar_id(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-template <int DH>
-__global__ void __maxnreg__(104)   // 19 warps x 104 registers fit the register file (__launch_bounds__(608) would cap at 96)
-attn_fwd_2g_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
-  static_assert(DH == 64, "two-group forward: head dim 64 only");
-  constexpr int KB = DH / 32;
-  constexpr int TILE_BYTES = 128 * DH * 4;
-  constexpr int KBLK_BYTES = 128 * 128;
-  constexpr int OC = DH / 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ks = smem + TILE_BYTES;            // [2]
-  uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
-  uint8_t* obox = smem + 5 * TILE_BYTES;      // [8 warps of group 0][4 KB] output store boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* s_full = bars + 10;   // [2] = per group
-  uint64_t* p_full = bars + 12;   // [2] = per group, 8 arrivals
-  uint64_t* o_full = bars + 14;   // [2] = per group: P_j V_j committed
-  uint64_t* sfree = bars + 16;    // [2]
-  uint64_t* o_free = bars + 18;   // both O tiles of the item read out by group 0 (8 arrivals)
-  uint64_t* g1_done = bars + 19;  // group 1 has published (max, sum) of the item (8 arrivals)
-  uint64_t* g1_read = bars + 20;  // group 0 has read them (8 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* xch = reinterpret_cast<float*>(bars + 24);   // per group [2][2][128] tile max + [2][128] row sum = 768 floats; then g1 (m, l) [2][128]
-  float* g1_ml = xch + 2 * 768;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    mbar_init(o_free, 8); mbar_init(g1_done, 8); mbar_init(g1_read, 8);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
-      mbar_init(&o_full[s], 1); mbar_init(&sfree[s], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int inner = p.heads * DH;
-  const int T = p.kv_tiles;
-
-  if (warp == 0) {
-    // ---- TMA producer (as in attn_fwd_tc_kernel)
-    uint32_t kv_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      const int qt = w % p.q_tiles;
-      const int bh = w / p.q_tiles;
-      const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(q_empty, (item_it & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, TILE_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) tma_load_3d(Qs + kb * KBLK_BYTES, &tmQK, q_full, h * DH + kb * 32, qt * 128, b);
-      }
-      __syncwarp();
-      for (int j = 0; j < T; ++j, ++kv_it) {
-        const int s = kv_it & 1;
-        const uint32_t ph = (kv_it >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-#pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(Ks + s * TILE_BYTES + kb * KBLK_BYTES, &tmQK, &k_full[s], inner + h * DH + kb * 32, j * 128, b);
-        }
-        __syncwarp();
-        mbar_wait(&v_empty[s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-          tma_load_4d(Vs + s * TILE_BYTES, &tmV, &v_full[s], 0, j * 128, (2 * inner + h * DH) / 32, b);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ---- issuer A: S_j = Q K_j^T into buffer j & 1.  NOTE: the buffer index must follow the tile parity *within the item*
-    // (group g owns tiles j = g mod 2), so items with an odd tile count restart at buffer 0: the ring counters below are
-    // per buffer, not a single running counter.
-    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);
-    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
-    const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
-    uint32_t kv_it = 0, item_it = 0;
-    uint32_t use0 = 0, use1 = 0;                   // how often S buffer 0 / 1 has been filled so far (scalars: no local-memory array)
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(q_full, item_it & 1);
-      for (int j = 0; j < T; ++j, ++kv_it) {
-        const int st = kv_it & 1;                  // K/V smem stage: plain ring over all tiles
-        const int g = j & 1;                       // S buffer / softmax group
-        mbar_wait(&k_full[st], (kv_it >> 1) & 1);
-        const uint32_t ug = g ? use1 : use0;
-        mbar_wait(&sfree[g], (ug & 1) ^ 1);        // the group's previous P has been consumed by issuer B
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t kd = desc_advance(kd0, st * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < DH / 8; ++k) {
-            const uint32_t off = (k >> 2) * KBLK_BYTES + (k & 3) * 32;
-            umma_tf32<1>(tmem_base + g * 128, desc_advance(qd, off), desc_advance(kd, off), idesc_s, k != 0);
-          }
-          umma_commit<1>(&s_full[g]);
-          umma_commit<1>(&k_empty[st]);
-          if (j == T - 1) umma_commit<1>(q_empty);
-        }
-        __syncwarp();
-        if (g) ++use1; else ++use0;
-      }
-    }
-  } else if (warp == kIssuerB) {
-    // ---- issuer B: O_g += P_j V_j (A from TMEM), one accumulator per group and item
-    constexpr uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);
-    const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
-    uint32_t kv_it = 0, item_it = 0;
-    uint32_t use0 = 0, use1 = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      for (int j = 0; j < T; ++j, ++kv_it) {
-        const int st = kv_it & 1;
-        const int g = j & 1;
-        mbar_wait(&v_full[st], (kv_it >> 1) & 1);
-        if (j == 0) mbar_wait(o_free, (item_it & 1) ^ 1);        // previous item's O tiles have been read out
-        const uint32_t ug = g ? use1 : use0;
-        mbar_wait(&p_full[g], ug & 1);                           // P_j stored (and O_g rescaled if needed)
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t vd = desc_advance(vd0, st * TILE_BYTES);
-          const uint32_t acc_on = j >= 2;                        // first tile of each group starts its accumulator
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_tf32_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + k * 8, desc_advance(vd, k * 1024), idesc_o, acc_on | (k != 0));
-          umma_commit<1>(&o_full[g]);
-          umma_commit<1>(&v_empty[st]);
-          umma_commit<1>(&sfree[g]);
-        }
-        __syncwarp();
-        if (g) ++use1; else ++use0;
-      }
-    }
-  } else {
-    // ---- softmax groups
-    const int g = warp > kIssuerB ? 1 : 0;
-    const int gw = g ? warp - 11 : warp - 2;            // 0..7 inside the group
-    const int q = warp & 3;                             // TMEM lane quarter this warp may touch
-    // the two warps of a group that share lane quarter q: group 0 -> warps q' and q'+4 of 2..9, group 1 -> of 11..18.
-    // Which of the two this warp is (column half 0 / 1) = whether it is the first or second warp with this (warp & 3).
-    const int first_with_q = g ? 11 + ((q - 3) & 3) : 2 + ((q - 2) & 3);
-    const int hf = warp == first_with_q ? 0 : 1;
-    const int bar_id = 2 + g * 4 + q;                   // named barriers 2..9 (64 threads each)
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const int row_in_tile = q * 32 + lane;
-    const float c = p.scale * kLog2eF;
-    float* gx = xch + g * 768;                          // this group's exchange area
-    uint32_t use = 0;                                   // tiles this group has processed so far (ring phase of its barriers)
-    uint32_t item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      const int qt = w % p.q_tiles;
-      const int bh = w / p.q_tiles;
-      const int h = bh % p.heads, b = bh / p.heads;
-      float m_run = -INFINITY, m_ref = 0.f, l = 0.f;
-      int jl = 0;                                       // tiles of this item done by this group
-      for (int j = g; j < T; j += 2, ++use, ++jl) {
-        mbar_wait(&s_full[g], use & 1);
-        tcgen05_fence_after();
-        const uint32_t sa = tmem_base + lane_off + g * 128 + hf * 64;
-        const int kv_left = p.N - j * 128 - hf * 64;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(sa, v0);
-        tmem_ld_32x32(sa + 32, v1);
-        tmem_ld_wait();
-        if (kv_left < 64) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_left) v0[i] = 0xff800000u;
-            if (32 + i >= kv_left) v1[i] = 0xff800000u;
-          }
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        float* xs = gx + (use & 1) * 256;
-        xs[hf * 128 + row_in_tile] = mx;
-        pair_bar_id(bar_id);
-        mx = fmaxf(mx, xs[(hf ^ 1) * 128 + row_in_tile]);
-        m_run = fmaxf(m_run, mx);
-        bool need = false;
-        if (jl == 0) m_ref = m_run;
-        else need = (m_run - m_ref) * c > 8.f;
-        if (__any_sync(0xffffffffu, need)) {            // lazy rescale of O_g (see attn_fwd_otmem_kernel)
-          mbar_wait(&o_full[g], (use - 1) & 1);         // this group's previous P.V has landed
-          tcgen05_fence_after();
-          const float alpha = need ? ex2_approx((m_ref - m_run) * c) : 1.f;
-          uint32_t ov[OC];
-          tmem_ld_32x32(tmem_base + lane_off + 256 + g * 64 + hf * OC, ov);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < OC; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st_32x32(tmem_base + lane_off + 256 + g * 64 + hf * OC, ov);
-          tmem_st_wait();
-          l *= alpha;
-          if (need) m_ref = m_run;
-        }
-        const float mc = m_ref * c;
-        float sum = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v0[i]), c, -mc));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v1[i]), c, -mc));
-          sum += e0; sum1 += e1;
-          v0[i] = tf32_bits_for_mma(e0);
-          v1[i] = tf32_bits_for_mma(e1);
-        }
-        l += sum + sum1;
-        tmem_st_32x32(sa, v0);
-        tmem_st_32x32(sa + 32, v1);
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
-      }
-      // ---- end of item: row sum of the group (both column halves), then the merge by group 0
-      float* ls = gx + 512;
-      ls[hf * 128 + row_in_tile] = l;
-      pair_bar_id(bar_id);
-      l += ls[(hf ^ 1) * 128 + row_in_tile];
-      if (g == 1) {
-        mbar_wait(g1_read, (item_it & 1) ^ 1);          // group 0 has consumed the previous item's values
-        if (hf == 0) {
-          g1_ml[row_in_tile] = jl > 0 ? m_ref : -INFINITY;
-          g1_ml[128 + row_in_tile] = jl > 0 ? l : 0.f;
-        }
-        pair_bar_id(bar_id);                            // ls free for the next item; the hf==0 stores are ordered before the arrive
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(g1_done);
-      } else {
-        // group 0 always has >= 1 tile (T >= 1)
-        mbar_wait(&o_full[0], (use - 1) & 1);
-        if (T > 1) {
-          // group 1's last tile of this item: its o_full phase counter equals the number of tiles it has done in total
-          mbar_wait(g1_done, item_it & 1);
-        }
-        tcgen05_fence_after();
-        float mB = -INFINITY, lB = 0.f;
-        if (T > 1) { mB = g1_ml[row_in_tile]; lB = g1_ml[128 + row_in_tile]; }
-        const float m_f = fmaxf(m_ref, mB);
-        const float wA = ex2_approx((m_ref - m_f) * c);
-        const float wB = T > 1 ? ex2_approx((mB - m_f) * c) : 0.f;
-        const float l_f = l * wA + lB * wB;
-        float o[OC];
-        {
-          uint32_t oa[OC];
-          tmem_ld_32x32(tmem_base + lane_off + 256 + hf * OC, oa);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(oa[i]) * wA;
-        }
-        if (T > 1) {
-          // group 1's P.V of its last tile: issuer B commits o_full[1] after it; wait for that commit here
-          // (group 0 does not otherwise track o_full[1]'s phase: it is the number of group-1 tiles so far, minus one)
-          const uint32_t g1_tiles_before = item_it * (uint32_t)(T / 2);           // tiles group 1 did in earlier items of THIS CTA
-          mbar_wait(&o_full[1], (g1_tiles_before + (uint32_t)(T / 2) - 1) & 1);
-          tcgen05_fence_after();
-          uint32_t ob[OC];
-          tmem_ld_32x32(tmem_base + lane_off + 256 + 64 + hf * OC, ob);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < OC; ++i) o[i] = fmaf(__uint_as_float(ob[i]), wB, o[i]);
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(o_free); mbar_arrive(g1_read); }
-        const int row = qt * 128 + row_in_tile;
-        const float inv = 1.f / l_f;
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = p.round_out ? round_tf32(o[i] * inv) : o[i] * inv;
-        warp_store_box(obox + gw * 4096, &tmO, o, h * DH + hf * OC, qt * 128 + q * 32, b, lane);
-        if (row < p.N && hf == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m_f * p.scale + logf(l_f);
-        pair_bar_id(bar_id);                            // ls is rewritten by the next item only after the partner has read it
-      }
-    }
-    if (g == 0 && lane == 0) bulk_wait_group_read<0>();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
-  }
-}
-
-template <int DH>
-static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, int round_out,
-                              cudaStream_t stream) {
+static int attn_fwd_tc_launch(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, float scale,
+                              int round_out, cudaStream_t stream) {
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
   CUtensorMap tmQK, tmV;
@@ -1005,45 +439,25 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
     if (rc) return rc;
   }
   AttnTcParams p;
-  p.out = out; p.lse = lse; p.B = B; p.N = N; p.heads = heads;
+  p.out = static_cast<float*>(out); p.out_half = out_half; p.lse = lse; p.B = B; p.N = N; p.heads = heads;
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale; p.round_out = round_out;
   CUtensorMap tmO;
   {
     const unsigned long long dims[3] = {(unsigned long long)inner, (unsigned long long)N, (unsigned long long)B};
-    const unsigned long long strides[2] = {(unsigned long long)inner * 4, (unsigned long long)N * inner * 4};
+    const unsigned long long esz = out_half ? 2 : 4;
+    const unsigned long long strides[2] = {(unsigned long long)inner * esz, (unsigned long long)N * inner * esz};
     const unsigned box[3] = {32, 32, 1};
-    int rc = make_tensor_map_f32(&tmO, out, 3, dims, strides, box, 0);
+    int rc = make_tensor_map(&tmO, out, (int)esz, 3, dims, strides, box, out_half ? 3 : 0);
     if (rc) return rc;
   }
   int grid = num_sms();
+  if (sm_limit() > 0 && grid > sm_limit()) grid = sm_limit();
   if (grid > p.total_items) grid = p.total_items;
   constexpr int smem = 5 * 128 * DH * 4 + kOutBoxBytes + 512 + 3 * 256 * 4 + 1024;
   auto kern = attn_fwd_tc_kernel<DH>;
-  static bool configured = false;
-  if (!configured) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
-  static const bool otmem = [] { const char* e = getenv("B200VQ_ATTN_FWD"); return e && e[0] == 'o'; }();
-  static const bool twog = [] { const char* e = getenv("B200VQ_ATTN_FWD"); return e && e[0] == '2'; }();
-  if constexpr (DH == 64) {
-    if (twog) {   // PROTOTYPE path, see attn_fwd_2g_kernel
-      constexpr int smem2 = 5 * 128 * DH * 4 + kOutBoxBytes + 256 + (2 * 768 + 256) * 4 + 1024;
-      auto kern3 = attn_fwd_2g_kernel<DH>;
-      static bool configured3 = false;
-      if (!configured3) { B200_CUDA_OK(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2)); configured3 = true; }
-      kern3<<<grid, kAtc2gThreads, smem2, stream>>>(tmQK, tmV, tmO, p);
-      B200_LAUNCH_OK("attn_fwd_2g_kernel");
-      return 0;
-    }
-    if (otmem) {   // PROTOTYPE path, see attn_fwd_otmem_kernel
-      auto kern2 = attn_fwd_otmem_kernel<DH>;
-      static bool configured2 = false;
-      if (!configured2) { B200_CUDA_OK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured2 = true; }
-      kern2<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, tmO, p);
-      B200_LAUNCH_OK("attn_fwd_otmem_kernel");
-      return 0;
-    }
-  }
+  B200_CONFIGURE_SMEM_ONCE(kern, smem);
   kern<<<grid, kAtcThreads, smem, stream>>>(tmQK, tmV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_tc_kernel");
   return 0;
@@ -1066,7 +480,9 @@ static int attn_fwd_tc_launch(const float* qkv, float* out, float* lse, int B, i
 struct AttnBwdParams {
   const float* lse;     // [B*heads*N]
   const float* delta;   // [B*heads*N]
-  float* dqkv;          // [B*N, 3*heads*DH]
+  float* dqkv;          // [B*N, 3*heads*DH] fp32, or fp16 when out_half
+  int out_half;         // 1: dqkv feeds fp16 GEMMs: store fp16, multiplied by *out_scale (the gradient scale)
+  const float* out_scale;
   int B, N, heads;
   int tiles128, sub64, total_items;
   float scale;
@@ -1303,16 +719,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
       const int col0 = (half == 0 ? 2 * inner : inner) + h * DH;
-      const float mul = half == 0 ? 1.f : p.scale;
+      const float mul = (half == 0 ? 1.f : p.scale) * (p.out_half && p.out_scale ? __ldg(p.out_scale) : 1.f);
 #pragma unroll 1
       for (int cc = 0; cc < DH / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_off + (half == 0 ? 256 : 320) + cc * 32, v);
         tmem_ld_wait();
         float r[32];
+        if (p.out_half) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * mul) : __uint_as_float(v[j]) * mul;
-        warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, col0 + cc * 32, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+          warp_store_box_h(obox + (warp - 2) * 4096, &tmOut, r, mul, col0 + cc * 32, kt * 128 + q * 32, b, lane);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * mul) : __uint_as_float(v[j]) * mul;
+          warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, col0 + cc * 32, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1529,9 +951,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         tmem_ld_wait();
         if constexpr (OC == 32) {
           float r[32];
+          if (p.out_half) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * p.scale) : __uint_as_float(v[j]) * p.scale;
-          warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+            for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+            warp_store_box_h(obox + (warp - 2) * 4096, &tmOut, r, p.scale * (p.out_scale ? __ldg(p.out_scale) : 1.f), h * DH + half * OC,
+                             qt * 128 + q * 32, b, lane);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = p.round_out ? round_tf32(__uint_as_float(v[j]) * p.scale) : __uint_as_float(v[j]) * p.scale;
+            warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+          }
+        } else if (row < p.N && p.out_half) {
+          const float mul = p.scale * (p.out_scale ? __ldg(p.out_scale) : 1.f);
+          __half* hp = reinterpret_cast<__half*>(p.dqkv) + ((long long)b * p.N + row) * (3ll * inner) + h * DH + half * OC;
+#pragma unroll
+          for (int j = 0; j < OC; j += 8) {
+            uint4 pk;
+            pk.x = pack_half2_sat(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul);
+            pk.y = pack_half2_sat(__uint_as_float(v[j + 2]) * mul, __uint_as_float(v[j + 3]) * mul);
+            pk.z = pack_half2_sat(__uint_as_float(v[j + 4]) * mul, __uint_as_float(v[j + 5]) * mul);
+            pk.w = pack_half2_sat(__uint_as_float(v[j + 6]) * mul, __uint_as_float(v[j + 7]) * mul);
+            *reinterpret_cast<uint4*>(hp + j) = pk;
+          }
         } else if (row < p.N) {
 #pragma unroll
           for (int j = 0; j < OC; j += 4) {
@@ -1539,255 +980,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
                                    __uint_as_float(v[j + 2]) * p.scale, __uint_as_float(v[j + 3]) * p.scale);
             if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
             *reinterpret_cast<float4*>(dqp + j) = a;
-          }
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-    }
-    if (lane == 0) bulk_wait_group_read<0>();   // the store boxes must outlive the last TMA reads
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// PROTOTYPE (round 2, not validated on hardware yet; selected with B200VQ_ATTN_DQ=128):
-// dQ kernel with 128-key tiles.  An M=128 tf32 MMA instruction costs max(N/2, ~48) cycles, so the
-// 64-key sub-tiles of the kernel above pay 48 cycles for 32 cycles of math on every score MMA.  Here
-//     S  = Q K_j^T, dP = dO V_j^T          N = 128: 8 + 8 instructions x 64 cycles
-//     dQ += dS_j K_j                       K-dim 128: 16 instructions x 48 cycles     = 1792 cycles / 128 keys
-// against 2 x 1152 before.  TMEM: S [0,128) single-buffered (dead as soon as the softmax warps have loaded it:
-// `s_free`), dP/dS [128,256) / [256,384) double-buffered (released by the dQ MMAs: `dp_free`), dQ [384,448).
-// Shared memory: Q, dO (K-major) + ONE stage of K (K-major), V (K-major), K (MN-major); the stage's buffers are
-// released at different times (kk_empty after the score MMAs, km_empty after the dQ MMAs), so the loads of tile
-// j+1 still overlap the softmax of tile j.
-template <int DH>
-__global__ void __launch_bounds__(kAtcThreads, 1)
-attn_bwd_dq128_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
-                         const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmKM128,
-                         const __grid_constant__ CUtensorMap tmOut, const AttnBwdParams p) {
-  constexpr int KB = DH / 32;
-  constexpr int T128 = 128 * DH * 4;
-  constexpr int KBLK128 = 128 * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ds = smem + T128;
-  uint8_t* KKs = smem + 2 * T128;       // K tile, K-major
-  uint8_t* VKs = smem + 3 * T128;       // V tile, K-major
-  uint8_t* KMs = smem + 4 * T128;       // K tile, MN-major
-  uint8_t* obox = smem + 5 * T128;      // [8 softmax warps][4 KB] output store boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kOutBoxBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* kk_full = bars + 2;
-  uint64_t* kk_empty = bars + 3;
-  uint64_t* km_full = bars + 4;
-  uint64_t* km_empty = bars + 5;
-  uint64_t* s_full = bars + 6;     // [2] indexed by the dP buffer of the tile
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* dp_free = bars + 10;   // [2] dS buffer consumed by issuer B
-  uint64_t* s_free = bars + 12;    // S loaded into registers by all 8 softmax warps
-  uint64_t* acc_full = bars + 13;
-  uint64_t* acc_empty = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmKV128); tma_prefetch_desc(&tmKM128);
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    mbar_init(kk_full, 1); mbar_init(kk_empty, 1);
-    mbar_init(km_full, 1); mbar_init(km_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); mbar_init(&dp_free[s], 1); }
-    mbar_init(s_free, 8);
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int inner = p.heads * DH;
-  const int T = p.tiles128;            // key tiles of 128
-
-  if (warp == 0) {
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      const int qt = w % p.tiles128;
-      const int bh = w / p.tiles128;
-      const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(q_empty, (item_it & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, 2 * T128);
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          tma_load_3d(Qs + kb * KBLK128, &tmQ128, q_full, h * DH + kb * 32, qt * 128, b);
-          tma_load_3d(Ds + kb * KBLK128, &tmDO128, q_full, h * DH + kb * 32, qt * 128, b);
-        }
-      }
-      __syncwarp();
-      for (int j = 0; j < T; ++j, ++t_it) {
-        const uint32_t ph = t_it & 1;
-        mbar_wait(kk_empty, ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(kk_full, 2 * T128);
-#pragma unroll
-          for (int kb = 0; kb < KB; ++kb) {
-            tma_load_3d(KKs + kb * KBLK128, &tmKV128, kk_full, inner + h * DH + kb * 32, j * 128, b);
-            tma_load_3d(VKs + kb * KBLK128, &tmKV128, kk_full, 2 * inner + h * DH + kb * 32, j * 128, b);
-          }
-        }
-        __syncwarp();
-        mbar_wait(km_empty, ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(km_full, T128);
-          tma_load_4d(KMs, &tmKM128, km_full, 0, j * 128, (inner + h * DH) / 32, b);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ---- issuer A: S = Q K^T, dP = dO V^T   (N = 128)
-    constexpr uint32_t idesc_s = make_idesc_tf32(128, 128, 0, 0);
-    const uint64_t qd = make_smem_desc(smem_u32(Qs), 16, 1024, kLayoutSw128);
-    const uint64_t dd = make_smem_desc(smem_u32(Ds), 16, 1024, kLayoutSw128);
-    const uint64_t kkd = make_smem_desc(smem_u32(KKs), 16, 1024, kLayoutSw128);
-    const uint64_t vkd = make_smem_desc(smem_u32(VKs), 16, 1024, kLayoutSw128);
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(q_full, item_it & 1);
-      for (int j = 0; j < T; ++j, ++t_it) {
-        const int s = t_it & 1;
-        mbar_wait(kk_full, t_it & 1);
-        mbar_wait(s_free, (t_it & 1) ^ 1);                 // S of the previous tile is in registers
-        mbar_wait(&dp_free[s], ((t_it >> 1) & 1) ^ 1);     // dS of tile t_it-2 consumed by the dQ MMAs
-        tcgen05_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < DH / 8; ++k) {
-            const uint32_t off = (k >> 2) * KBLK128 + (k & 3) * 32;
-            umma_tf32<1>(tmem_base, desc_advance(qd, off), desc_advance(kkd, off), idesc_s, k != 0);
-          }
-#pragma unroll
-          for (int k = 0; k < DH / 8; ++k) {
-            const uint32_t off = (k >> 2) * KBLK128 + (k & 3) * 32;
-            umma_tf32<1>(tmem_base + 128 + s * 128, desc_advance(dd, off), desc_advance(vkd, off), idesc_s, k != 0);
-          }
-          umma_commit<1>(&s_full[s]);
-          umma_commit<1>(kk_empty);
-          if (j == T - 1) umma_commit<1>(q_empty);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == kIssuerB) {
-    // ---- issuer B: dQ += dS K (A operand from TMEM, K-dim = 128 keys)
-    constexpr uint32_t idesc_g = make_idesc_tf32(128, DH, 0, 1);
-    const uint64_t kmd = make_smem_desc(smem_u32(KMs), KBLK128, 512, kLayoutSw128Base32);
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      for (int j = 0; j < T; ++j, ++t_it) {
-        const int s = t_it & 1;
-        mbar_wait(km_full, t_it & 1);
-        if (j == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        mbar_wait(&p_full[s], (t_it >> 1) & 1);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t acc_on = j > 0;
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_tf32_ts(tmem_base + 384, tmem_base + 128 + s * 128 + k * 8, desc_advance(kmd, k * 1024), idesc_g, acc_on | (k != 0));
-          umma_commit<1>(km_empty);
-          umma_commit<1>(&dp_free[s]);
-          if (j == T - 1) umma_commit<1>(acc_full);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // softmax warps: thread = query row, warps w and w+4 split the 128 key columns of a tile in halves of 64,
-    // each processed in two passes of 32 columns (register budget)
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int OC = DH / 2;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const float c = p.scale * kLog2eF;
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      const int qt = w % p.tiles128;
-      const int bh = w / p.tiles128;
-      const int h = bh % p.heads, b = bh / p.heads;
-      const int row = qt * 128 + q * 32 + lane;
-      const long long sidx = ((long long)b * p.heads + h) * p.N + row;
-      const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
-      const float dl = row < p.N ? p.delta[sidx] : 0.f;
-      for (int j = 0; j < T; ++j, ++t_it) {
-        const int s = t_it & 1;
-        mbar_wait(&s_full[s], (t_it >> 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t s_addr = tmem_base + lane_off + half * 64;
-        const uint32_t g_addr = tmem_base + lane_off + 128 + s * 128 + half * 64;
-        uint32_t v[32], g[32], v2[32];
-        tmem_ld_32x32(s_addr, v);
-        tmem_ld_32x32(s_addr + 32, v2);
-        tmem_ld_32x32(g_addr, g);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);            // the S buffer may be overwritten by the next tile's score MMA
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int kv_left = p.N - j * 128 - half * 64 - pass * 32;
-          if (pass == 1) {
-            tmem_ld_32x32(g_addr + 32, g);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = v2[i];
-          }
-          if (kv_left >= 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              g[i] = tf32_bits_for_mma(ex2_approx(fmaf(__uint_as_float(v[i]), c, -lse2)) * (__uint_as_float(g[i]) - dl));
-          } else {                                    // ragged last tile: padded key columns contribute nothing
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float pr = (i < kv_left) ? ex2_approx(fmaf(__uint_as_float(v[i]), c, -lse2)) : 0.f;
-              g[i] = tf32_bits_for_mma(pr * (__uint_as_float(g[i]) - dl));
-            }
-          }
-          tmem_st_32x32(g_addr + pass * 32, g);
-          tmem_st_wait();
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
-      }
-      mbar_wait(acc_full, item_it & 1);
-      tcgen05_fence_after();
-      float* dqp = p.dqkv + ((long long)b * p.N + row) * (3ll * inner) + h * DH + half * OC;
-      {
-        uint32_t v[OC];
-        tmem_ld_cols<OC>(tmem_base + lane_off + 384 + half * OC, v);
-        tmem_ld_wait();
-        if constexpr (OC == 32) {
-          float r[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = p.round_out ? round_tf32(__uint_as_float(v[i]) * p.scale) : __uint_as_float(v[i]) * p.scale;
-          warp_store_box(obox + (warp - 2) * 4096, &tmOut, r, h * DH + half * OC, qt * 128 + q * 32, b, lane);
-        } else if (row < p.N) {
-#pragma unroll
-          for (int i = 0; i < OC; i += 4) {
-            float4 a = make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
-                                   __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
-            if (p.round_out) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
-            *reinterpret_cast<float4*>(dqp + i) = a;
           }
         }
       }
@@ -1821,13 +1013,18 @@ static int make_mnmajor_map(CUtensorMap* out, const float* ptr, long long ld, in
 }
 
 template <int DH>
-static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B,
-                              int N, int heads, float scale, int round_out, cudaStream_t stream) {
+static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* lse, const float* delta, void* dqkv, int out_half,
+                              const float* out_scale, int B, int N, int heads, float scale, int round_out, cudaStream_t stream) {
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
   CUtensorMap tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmDO128, tmOut;
   int rc;
-  if ((rc = make_kmajor_map(&tmOut, dqkv, ld, N, B, 32))) return rc;
+  if (out_half) {   // {ld, N, B} fp16 view, 32 x 32 un-swizzled store boxes
+    const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
+    const unsigned long long strides[2] = {(unsigned long long)ld * 2, (unsigned long long)N * ld * 2};
+    const unsigned box[3] = {32, 32, 1};
+    if ((rc = make_tensor_map(&tmOut, dqkv, 2, 3, dims, strides, box, 3))) return rc;
+  } else if ((rc = make_kmajor_map(&tmOut, static_cast<const float*>(dqkv), ld, N, B, 32))) return rc;
   if ((rc = make_kmajor_map(&tmKV128, qkv, ld, N, B, 128))) return rc;
   if ((rc = make_kmajor_map(&tmQ64, qkv, ld, N, B, 64))) return rc;
   if ((rc = make_kmajor_map(&tmDO64, dout, inner, N, B, 64))) return rc;
@@ -1835,7 +1032,8 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   if ((rc = make_mnmajor_map(&tmQM, qkv, ld, N, B, 64, DH / 32))) return rc;
   if ((rc = make_mnmajor_map(&tmDOM, dout, inner, N, B, 64, DH / 32))) return rc;
   AttnBwdParams p;
-  p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.B = B; p.N = N; p.heads = heads;
+  p.lse = lse; p.delta = delta; p.dqkv = static_cast<float*>(dqkv); p.out_half = out_half; p.out_scale = out_scale;
+  p.B = B; p.N = N; p.heads = heads;
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale; p.round_out = round_out;
@@ -1843,28 +1041,13 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + kOutBoxBytes + 256 + 1024;
   auto k1 = attn_bwd_dkv_tc_kernel<DH>;
   auto k2 = attn_bwd_dq_tc_kernel<DH>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    B200_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
-    configured = true;
-  }
+  B200_CONFIGURE_SMEM_ONCE(k1, smem_kv);
+  B200_CONFIGURE_SMEM_ONCE(k2, smem_q);
   int grid = num_sms();
+  if (sm_limit() > 0 && grid > sm_limit()) grid = sm_limit();
   if (grid > p.total_items) grid = p.total_items;
   k1<<<grid, kAtcThreads, smem_kv, stream>>>(tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  static const bool dq128 = [] { const char* e = getenv("B200VQ_ATTN_DQ"); return e && e[0] == '1' && e[1] == '2' && e[2] == '8'; }();
-  if (dq128) {   // PROTOTYPE path, see attn_bwd_dq128_tc_kernel
-    CUtensorMap tmKM128;
-    if ((rc = make_mnmajor_map(&tmKM128, qkv, ld, N, B, 128, DH / 32))) return rc;
-    constexpr int smem_q128 = 5 * 128 * DH * 4 + kOutBoxBytes + 256 + 1024;
-    auto k3 = attn_bwd_dq128_tc_kernel<DH>;
-    static bool configured128 = false;
-    if (!configured128) { B200_CUDA_OK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q128)); configured128 = true; }
-    k3<<<grid, kAtcThreads, smem_q128, stream>>>(tmKV128, tmDO128, tmKV128, tmKM128, tmOut, p);
-    B200_LAUNCH_OK("attn_bwd_dq128_tc_kernel");
-    return 0;
-  }
   k2<<<grid, kAtcThreads, smem_q, stream>>>(tmKV128, tmDO128, tmQ64, tmQM, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return 0;
@@ -1877,20 +1060,20 @@ extern "C" int b200vq_trace_read(long long* out) {   // out[3][2 * 36]: (event, 
 }
 #endif
 
-int attention_backward_tc(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B, int N,
-                          int heads, int dh, float scale, int round_out, cudaStream_t stream) {
+int attention_backward_tc(const float* qkv, const float* dout, const float* lse, const float* delta, void* dqkv, int out_half,
+                          const float* out_scale, int B, int N, int heads, int dh, float scale, int round_out, cudaStream_t stream) {
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
                  "attention: qkv/dout must be 16-byte aligned");
-  if (dh == 64) return attn_bwd_tc_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
-  return attn_bwd_tc_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, round_out, stream);
+  if (dh == 64) return attn_bwd_tc_launch<64>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, stream);
+  return attn_bwd_tc_launch<32>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, stream);
 }
 
-int attention_forward_tc(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale, int round_out,
-                         cudaStream_t stream) {
+int attention_forward_tc(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, int dh, float scale,
+                         int round_out, cudaStream_t stream) {
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "attention: qkv must be 16-byte aligned");
-  if (dh == 64) return attn_fwd_tc_launch<64>(qkv, out, lse, B, N, heads, scale, round_out, stream);
-  return attn_fwd_tc_launch<32>(qkv, out, lse, B, N, heads, scale, round_out, stream);
+  if (dh == 64) return attn_fwd_tc_launch<64>(qkv, out, out_half, lse, B, N, heads, scale, round_out, stream);
+  return attn_fwd_tc_launch<32>(qkv, out, out_half, lse, B, N, heads, scale, round_out, stream);
 }
 
 }  // namespace b200

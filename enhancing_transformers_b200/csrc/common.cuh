@@ -3,6 +3,7 @@
 // (SM100 shared-memory matrix descriptor, instruction descriptor, 2-SM TMA peer-bit mask).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,10 +37,31 @@ void count_launch();
       return ::b200::set_error(-3, "launch of %s failed: %s", name, cudaGetErrorString(e__));  \
   } while (0)
 
-int num_sms();
-// generic fp32 tiled tensor map (rank <= 5), cached; swizzle: 0 = SWIZZLE_128B, 1 = SWIZZLE_128B_ATOM_32B
-int make_tensor_map_f32(CUtensorMap* out, const float* ptr, int rank, const unsigned long long* dims,
-                        const unsigned long long* strides_bytes, const unsigned* box, int swizzle_base32);
+int num_sms();            // SM count of the *current* device (cached per device)
+int current_device();     // cudaGetDevice, or -1
+int sm_limit();           // 0 = none; otherwise persistent kernels launch at most this many CTAs (leaves SMs to NCCL)
+// Per-kernel, per-device one-time setup (cudaFuncSetAttribute is a per-device property: a process that drives
+// several GPUs -- DataParallel, a multi-device script -- must set it once on each of them).
+constexpr int kMaxDevices = 64;
+struct PerDevice { bool done[kMaxDevices] = {}; int value[kMaxDevices] = {}; };
+#define B200_CONFIGURE_SMEM_ONCE(kern, bytes)                                                                \
+  do {                                                                                                       \
+    static ::b200::PerDevice once__;                                                                         \
+    const int dev__ = ::b200::current_device();                                                              \
+    if (dev__ < 0 || dev__ >= ::b200::kMaxDevices) return ::b200::set_error(-2, "no current CUDA device");   \
+    if (!once__.done[dev__]) {                                                                               \
+      B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      once__.done[dev__] = true;                                                                             \
+    }                                                                                                        \
+  } while (0)
+// generic tiled tensor map (rank <= 5), cached.  elem_bytes: 4 = fp32, 2 = fp16;
+// swizzle: 0 = SWIZZLE_128B, 1 = SWIZZLE_128B_ATOM_32B (MN-major tf32 operands), 2 = SWIZZLE_64B, 3 = none
+int make_tensor_map(CUtensorMap* out, const void* ptr, int elem_bytes, int rank, const unsigned long long* dims,
+                    const unsigned long long* strides_bytes, const unsigned* box, int swizzle);
+inline int make_tensor_map_f32(CUtensorMap* out, const float* ptr, int rank, const unsigned long long* dims,
+                               const unsigned long long* strides_bytes, const unsigned* box, int swizzle_base32) {
+  return make_tensor_map(out, ptr, 4, rank, dims, strides_bytes, box, swizzle_base32);
+}
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
@@ -242,6 +264,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, fp16 inputs (kind::f16), fp32 accumulate: UMMA_K = 16, twice the tf32 rate
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int KIND, int CG>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == 0) umma_tf32<CG>(d_tmem, adesc, bdesc, idesc, accumulate);
+  else                     umma_f16<CG>(d_tmem, adesc, bdesc, idesc, accumulate);
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -331,6 +372,18 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_of
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// instruction descriptor for kind::f16 with fp16 inputs, fp32 accumulate: a_format = b_format = 0 (F16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// two fp32 -> packed fp16x2 (round to nearest), saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 #endif  // __CUDACC__
 

@@ -14,8 +14,8 @@ constexpr float kLnEps = 1e-5f;
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
-              int round_out) {
+              float* __restrict__ y, __half* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              int M, int D, int round_out) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;
@@ -52,8 +52,15 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
         o.y = (v[i].y - mu) * rstd * g.y + b.y;
         o.z = (v[i].z - mu) * rstd * g.z + b.z;
         o.w = (v[i].w - mu) * rstd * g.w + b.w;
-        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        yr[c] = o;
+        if (y16) {   // the normalised row only feeds an fp16 GEMM: 8 bytes per 4 values
+          uint2 pk;
+          pk.x = pack_half2_sat(o.x, o.y); pk.y = pack_half2_sat(o.z, o.w);
+          reinterpret_cast<uint2*>(y16 + (size_t)row * D)[c] = pk;
+        }
+        if (y) {
+          if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          yr[c] = o;
+        }
       }
     }
     if (lane == 0) {
@@ -76,8 +83,10 @@ template <int NV, int NACC>
 __global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
-              float* __restrict__ dx, float* __restrict__ part, int M, int D, int round_out) {
+              float* __restrict__ dx, __half* __restrict__ dx16, const float* __restrict__ scale_ptr,
+              float* __restrict__ part, int M, int D, int round_out) {
   extern __shared__ float sm[];   // [warps][NACC][D]
+  const float gscale = (dx16 && scale_ptr) ? __ldg(scale_ptr) : 1.f;   // gradient scale of the fp16 copy
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 2;
@@ -138,6 +147,11 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         o.y = rs * (g[i].y - m1 - xh[i].y * m2) + r[i].y;
         o.z = rs * (g[i].z - m1 - xh[i].z * m2) + r[i].z;
         o.w = rs * (g[i].w - m1 - xh[i].w * m2) + r[i].w;
+        if (dx16) {   // the same gradient, scaled, as the fp16 operand of the next dgrad / wgrad GEMMs
+          uint2 pk;
+          pk.x = pack_half2_sat(o.x * gscale, o.y * gscale); pk.y = pack_half2_sat(o.z * gscale, o.w * gscale);
+          reinterpret_cast<uint2*>(dx16 + (size_t)row * D)[c] = pk;
+        }
         if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         outr[c] = o;
         if (NACC == 3) {
@@ -220,13 +234,15 @@ colsum_kernel(const float* __restrict__ X, long long ld, int M, int N, float* __
 
 // out[i] = sum_z part[z][i] (+ bias-free), used after split-K wgrad
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long n4, long long stride4,
-                                     float* __restrict__ out) {
+                                     const float* __restrict__ alpha_ptr, float* __restrict__ out) {
+  const float alpha = alpha_ptr ? __ldg(alpha_ptr) : 1.f;   // undoes the gradient scale of fp16 wgrad operands
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<const float4*>(part)[i];
     for (int z = 1; z < splits; ++z) {
       const float4 v = reinterpret_cast<const float4*>(part)[i + z * stride4];
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
+    a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
     reinterpret_cast<float4*>(out)[i] = a;
   }
 }
@@ -236,6 +252,73 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
     float4 v = reinterpret_cast<const float4*>(in)[i];
     v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
     reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+// lo = x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates to 10 mantissa
+// bits); exact in fp32.  The 3xTF32 product adds A_lo.B + A.B_lo to A.B.
+__global__ void split_tf32_lo_kernel(const float* __restrict__ in, float* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    float4 o;
+    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    reinterpret_cast<float4*>(lo)[i] = o;
+  }
+}
+
+// out16 = fp16(in * scale), saturating (scale: device scalar or null)
+__global__ void to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n4,
+                               const float* __restrict__ scale_ptr) {
+  const float sc = scale_ptr ? __ldg(scale_ptr) : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    uint2 pk;
+    pk.x = pack_half2_sat(v.x * sc, v.y * sc); pk.y = pack_half2_sat(v.z * sc, v.w * sc);
+    reinterpret_cast<uint2*>(out)[i] = pk;
+  }
+}
+
+// Gradient scale of one backward segment: S = 2^(target_log2 - ceil(log2(max|g|))), the power of two that puts the
+// largest entry of the incoming gradient at ~2^target_log2, so that everything derived from it sits in fp16's
+// normal range (65504 = 2^16 at the top, 2^-14 at the bottom).  Stage 1: per-block |max| (bit pattern of a
+// non-negative float orders like an unsigned int); stage 2: one block -> scale2 = {S, 1/S}.
+__global__ void __launch_bounds__(256)
+absmax_part_kernel(const float* __restrict__ g, long long n4, unsigned* __restrict__ part) {
+  unsigned m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ unsigned red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+    part[blockIdx.x] = m;
+  }
+}
+__global__ void grad_scale_kernel(const unsigned* __restrict__ part, int nparts, int target_log2, float* __restrict__ scale2) {
+  unsigned m = 0;
+  for (int i = threadIdx.x; i < nparts; i += 32) m = max(m, part[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) {
+    const float amax = __uint_as_float(m);
+    float S = 1.f;
+    if (amax > 0.f && amax < INFINITY) {          // zero / inf / nan gradients: leave unscaled
+      int e;
+      frexpf(amax, &e);                          // amax = f * 2^e, f in [0.5, 1)  ->  amax <= 2^e
+      int sh = target_log2 - e;
+      sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+      S = ldexpf(1.f, sh);
+    }
+    scale2[0] = S;
+    scale2[1] = 1.f / S;
   }
 }
 
@@ -310,22 +393,24 @@ static inline int stream_grid(long long work_items, int threads) {
 }
 
 template <int NV>
-static void ln_fwd_launch(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int M, int D,
-                          int round_out, cudaStream_t s) {
+static void ln_fwd_launch(const float* x, const float* g, const float* b, float* y, __half* y16, float* mean, float* rstd, int M,
+                          int D, int round_out, cudaStream_t s) {
   const int blocks = stream_grid((long long)M * 32, 256);
-  ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, g, b, y, mean, rstd, M, D, round_out);
+  ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, g, b, y, y16, mean, rstd, M, D, round_out);
 }
 
-int layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M,
-                      int D, int round_out, cudaStream_t stream) {
+int layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, void* y16v, float* mean, float* rstd,
+                      int M, int D, int round_out, cudaStream_t stream) {
   B200_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm: need D %% 4 == 0 and D <= 2048 (D=%d)", D);
+  B200_CHECK_ARG(y || y16v, "layernorm: no output buffer");
+  __half* y16 = static_cast<__half*>(y16v);
   const int nv = (D + 127) / 128;
-  if (nv <= 1) ln_fwd_launch<1>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
-  else if (nv <= 2) ln_fwd_launch<2>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
-  else if (nv <= 4) ln_fwd_launch<4>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
-  else if (nv <= 6) ln_fwd_launch<6>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
-  else if (nv <= 10) ln_fwd_launch<10>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
-  else ln_fwd_launch<16>(x, gamma, beta, y, mean, rstd, M, D, round_out, stream);
+  if (nv <= 1) ln_fwd_launch<1>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 2) ln_fwd_launch<2>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 4) ln_fwd_launch<4>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 6) ln_fwd_launch<6>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
+  else if (nv <= 10) ln_fwd_launch<10>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
+  else ln_fwd_launch<16>(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, stream);
   B200_LAUNCH_OK("ln_fwd_kernel");
   return 0;
 }
@@ -335,37 +420,40 @@ size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)layernorm_bwd_block
 
 template <int NV, int NACC>
 static int ln_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, float* part, int M, int D, int round_out, int blocks, cudaStream_t s) {
+                         const float* dres, float* dx, __half* dx16, const float* scale_ptr, float* part, int M, int D, int round_out,
+                         int blocks, cudaStream_t s) {
   const size_t smem = (size_t)8 * NACC * D * sizeof(float);
   auto kern = ln_bwd_kernel<NV, NACC>;
   if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, 256, smem, s>>>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out);
+  kern<<<blocks, 256, smem, s>>>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out);
   return 0;
 }
 
 template <int NACC>
 static int ln_bwd_dispatch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                           const float* dres, float* dx, float* part, int M, int D, int round_out, int blocks, cudaStream_t s) {
+                           const float* dres, float* dx, __half* dx16, const float* scale_ptr, float* part, int M, int D,
+                           int round_out, int blocks, cudaStream_t s) {
   const int nv = (D + 127) / 128;
-  if (nv <= 1) return ln_bwd_launch<1, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
-  if (nv <= 2) return ln_bwd_launch<2, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
-  if (nv <= 4) return ln_bwd_launch<4, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
-  if (nv <= 6) return ln_bwd_launch<6, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
-  if (nv <= 10) return ln_bwd_launch<10, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
-  return ln_bwd_launch<16, NACC>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, s);
+  if (nv <= 1) return ln_bwd_launch<1, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 2) return ln_bwd_launch<2, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 4) return ln_bwd_launch<4, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 6) return ln_bwd_launch<6, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 10) return ln_bwd_launch<10, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  return ln_bwd_launch<16, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
 }
 
 int layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D, int round_out,
-                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                       const float* dres, float* dx, void* dx16v, const float* scale_ptr, float* dgamma, float* dbeta,
+                       float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  __half* dx16 = static_cast<__half*>(dx16v);
   B200_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm: need D %% 4 == 0 and D <= 2048 (D=%d)", D);
   B200_CHECK_ARG(ws_bytes >= layernorm_bwd_workspace_bytes(D), "layernorm_backward: workspace too small");
   int blocks = layernorm_bwd_blocks();
   if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
   float* part = static_cast<float*>(workspace);
   const int nacc = dxsum ? 3 : 2;
-  int rc = dxsum ? ln_bwd_dispatch<3>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream)
-                 : ln_bwd_dispatch<2>(dy, x, mean, rstd, gamma, dres, dx, part, M, D, round_out, blocks, stream);
+  int rc = dxsum ? ln_bwd_dispatch<3>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream)
+                 : ln_bwd_dispatch<2>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream);
   if (rc) return rc;
   B200_LAUNCH_OK("ln_bwd_kernel");
   ln_param_reduce_kernel<<<(nacc * D + 255) / 256, 256, 0, stream>>>(part, blocks, D, nacc, dgamma, dbeta, dxsum);
@@ -392,9 +480,10 @@ int colsum(const float* X, long long ld, int M, int N, float* out, void* workspa
   return 0;
 }
 
-int splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, cudaStream_t stream) {
+int splitk_reduce(const float* part, int splits, long long n, long long split_stride, const float* alpha_ptr, float* out,
+                  cudaStream_t stream) {
   B200_CHECK_ARG(n % 4 == 0 && split_stride % 4 == 0, "splitk_reduce: sizes must be multiples of 4");
-  splitk_reduce_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(part, splits, n / 4, split_stride / 4, out);
+  splitk_reduce_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(part, splits, n / 4, split_stride / 4, alpha_ptr, out);
   B200_LAUNCH_OK("splitk_reduce_kernel");
   return 0;
 }
@@ -403,6 +492,36 @@ int round_tf32_copy(const float* in, float* out, long long n, cudaStream_t strea
   B200_CHECK_ARG(n % 4 == 0, "round_tf32: n %% 4");
   round_tf32_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(in, out, n / 4);
   B200_LAUNCH_OK("round_tf32_kernel");
+  return 0;
+}
+
+int split_tf32_lo(const float* in, float* lo, long long n, cudaStream_t stream) {
+  B200_CHECK_ARG(n % 4 == 0, "split_tf32_lo: n %% 4");
+  split_tf32_lo_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(in, lo, n / 4);
+  B200_LAUNCH_OK("split_tf32_lo_kernel");
+  return 0;
+}
+
+int to_half(const float* in, void* out, long long n, const float* scale_ptr, cudaStream_t stream) {
+  B200_CHECK_ARG(n % 4 == 0, "to_half: n %% 4");
+  to_half_kernel<<<stream_grid(n / 4, 256), 256, 0, stream>>>(in, static_cast<__half*>(out), n / 4, scale_ptr);
+  B200_LAUNCH_OK("to_half_kernel");
+  return 0;
+}
+
+constexpr int kAbsmaxBlocks = 1184;   // 148 SMs x 8
+size_t grad_scale_workspace_bytes() { return kAbsmaxBlocks * sizeof(unsigned); }
+int grad_scale(const float* g, long long n, int target_log2, float* scale2, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  B200_CHECK_ARG(n > 0 && n % 4 == 0, "grad_scale: n %% 4");
+  B200_CHECK_ARG(ws_bytes >= grad_scale_workspace_bytes(), "grad_scale: workspace too small");
+  B200_CHECK_ARG(target_log2 >= -14 && target_log2 <= 15, "grad_scale: target exponent outside the fp16 range");
+  int blocks = stream_grid(n / 4, 256);
+  if (blocks > kAbsmaxBlocks) blocks = kAbsmaxBlocks;
+  unsigned* part = static_cast<unsigned*>(workspace);
+  absmax_part_kernel<<<blocks, 256, 0, stream>>>(g, n / 4, part);
+  B200_LAUNCH_OK("absmax_part_kernel");
+  grad_scale_kernel<<<1, 32, 0, stream>>>(part, blocks, target_log2, scale2);
+  B200_LAUNCH_OK("grad_scale_kernel");
   return 0;
 }
 

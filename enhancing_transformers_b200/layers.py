@@ -132,17 +132,43 @@ class Transformer(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         batch, tokens, width = x.shape
-        h = _flat2d(x)
+        att0 = self.layers[0][0].fn if len(self.layers) else None
+        if att0 is not None and not isinstance(att0.to_out, nn.Linear):
+            # heads == 1 and dim_head == dim (reference layers.py:112,120: no output projection): the fused
+            # stack always has a to_out GEMM, so run the sub-modules one by one (same kernels, stand-alone units)
+            for pre_attn, pre_ff in self.layers:
+                x = Fn.AddFn.apply(pre_attn(x), x)
+                x = Fn.AddFn.apply(pre_ff(x), x)
+            h = Fn.LayerNormFn.apply(_flat2d(x), self.norm.weight, self.norm.bias, self.round_final)
+            return h.view(batch, tokens, width)
+        params = []
         for pre_attn, pre_ff in self.layers:
             att, ff = pre_attn.fn, pre_ff.fn
-            if not isinstance(att.to_out, nn.Linear):
-                raise NotImplementedError("heads == 1 and dim_head == dim (no output projection) is not built")
-            h = Fn.TransformerLayerFn.apply(
-                h, pre_attn.norm.weight, pre_attn.norm.bias, att.to_qkv.weight, att.to_out.weight, att.to_out.bias,
-                pre_ff.norm.weight, pre_ff.norm.bias, ff.net[0].weight, ff.net[0].bias, ff.net[2].weight, ff.net[2].bias,
-                batch, tokens, att.heads, att.dim_head)
-        h = Fn.LayerNormFn.apply(h, self.norm.weight, self.norm.bias, self.round_final)
+            params += [pre_attn.norm.weight, pre_attn.norm.bias, att.to_qkv.weight, att.to_out.weight, att.to_out.bias,
+                       pre_ff.norm.weight, pre_ff.norm.bias, ff.net[0].weight, ff.net[0].bias, ff.net[2].weight, ff.net[2].bias]
+        h = Fn.TransformerFn.apply(_flat2d(x), batch, tokens, self.heads, self.dim_head, self.round_final,
+                                   self.norm.weight, self.norm.bias, *params)
         return h.view(batch, tokens, width)
+
+
+class QuantLinear(nn.Linear):
+    """``pre_quant`` / ``post_quant`` of the unchanged ``ViTVQ`` (reference vitvqgan.py:38-39,63,69) on the
+    tcgen05 GEMM instead of cuBLAS.  Same parameters and state-dict keys as the ``nn.Linear`` it replaces
+    (`from_linear` shares them).  Always the error-compensated 3xTF32 product: ``pre_quant`` writes the
+    vector whose nearest code is looked up, so its rounding decides the indices, and both GEMMs are
+    memory-bound (K or N = 32) -- the extra tensor passes are free."""
+
+    @classmethod
+    def from_linear(cls, lin: nn.Linear) -> "QuantLinear":
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.in_features, new.out_features = lin.in_features, lin.out_features
+        new.weight, new.bias = lin.weight, lin.bias
+        return new
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = Fn.LinearFn.apply(_flat2d(x), self.weight, self.bias, 0, True)
+        return y.view(*x.shape[:-1], self.out_features)
 
 
 class _Geometry:

@@ -22,6 +22,12 @@ def _req(t: Optional[Tensor], name: str, dtype=torch.float32) -> None:
         raise RuntimeError(f"b200vq: `{name}` must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"b200vq: `{name}` must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's current stream: a tensor living elsewhere would be
+        # dereferenced on the wrong GPU (one process per GPU is the supported layout)
+        raise RuntimeError(f"b200vq: `{name}` lives on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device (or use "
+                           "`with torch.cuda.device_of(x):`) before invoking the module")
 
 
 def _p(t: Optional[Tensor]):
@@ -36,109 +42,205 @@ def launch_count() -> int:
     return int(_lib.lib().b200vq_launch_count())
 
 
+def set_sm_limit(n: int) -> None:
+    """cap the persistent GEMM / attention grids at n CTAs (0 = all SMs): leaves SMs to a concurrent NCCL kernel"""
+    _lib.lib().b200vq_set_sm_limit(int(n))
+
+
+_HALF = torch.float16
+
+
+def _req_any(t: Optional[Tensor], name: str) -> None:
+    _req(t, name, t.dtype if t is not None and t.dtype in (torch.float32, _HALF) else torch.float32)
+
+
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_major: int = 0, b_major: int = 0,
          lda: Optional[int] = None, ldb: Optional[int] = None, out: Optional[Tensor] = None,
          bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_row_mod: int = 0,
          aux: Optional[Tensor] = None, act: int = 0, round_out: bool = False, splits: int = 1,
-         cta_group: int = 1, bn: int = 0, want_colsum: bool = False):
-    """C[M,N] = epilogue(A . B^T).  See b200vq_gemm_tf32.  With splits > 1 returns [splits, M, N].
+         cta_group: int = 1, bn: int = 0, want_colsum: bool = False, a_lo: Optional[Tensor] = None,
+         b_lo: Optional[Tensor] = None, out_half: bool = False, alpha: Optional[Tensor] = None):
+    """C[M,N] = epilogue(alpha * A . B^T).  See include/b200vq.h.  With splits > 1 returns [splits, M, N].
+    The operand dtype picks the tensor-core flavour: fp32 -> b200vq_gemm_tf32 (or, with a_lo/b_lo, the
+    error-compensated b200vq_gemm_3xtf32), fp16 -> b200vq_gemm_f16 (out_half: fp16 C; alpha: device scalar).
     want_colsum: also return colsum(C) (-> (C, colsum)); the epilogue emits per-32-row partial sums."""
-    _req(a, "a"); _req(b, "b"); _req(bias, "bias"); _req(res, "res"); _req(aux, "aux")
+    half = a.dtype == _HALF
+    _req(a, "a", a.dtype if half else torch.float32); _req(b, "b", a.dtype)
+    _req(bias, "bias"); _req(res, "res"); _req(alpha, "alpha")
+    if aux is not None:
+        _req(aux, "aux", _HALF if out_half else torch.float32)
     if lda is None:
         lda = a.shape[-1]
     if ldb is None:
         ldb = b.shape[-1]
     if out is None:
-        out = torch.empty((splits, M, N) if splits > 1 else (M, N), device=a.device, dtype=torch.float32)
-    _req(out, "out")
+        out = torch.empty((splits, M, N) if splits > 1 else (M, N), device=a.device, dtype=_HALF if out_half else torch.float32)
+    _req(out, "out", _HALF if out_half else torch.float32)
     part = torch.empty((M + 31) // 32, N, device=a.device, dtype=torch.float32) if want_colsum else None
-    rc = _lib.lib().b200vq_gemm_tf32(_p(a), lda, a_major, _p(b), ldb, b_major, _p(out), N, M, N, K, splits, M * N,
-                                     _p(bias), _p(res), (res.shape[-1] if res is not None else 0), res_row_mod,
-                                     _p(aux), (aux.shape[-1] if aux is not None else 0), _p(part), act, int(round_out),
-                                     cta_group, bn, _stream())
-    _lib.check(rc, "gemm_tf32")
+    L = _lib.lib()
+    ldres = res.shape[-1] if res is not None else 0
+    ldaux = aux.shape[-1] if aux is not None else 0
+    if half:
+        if a_lo is not None or b_lo is not None:
+            raise RuntimeError("b200vq: the 3xTF32 product takes fp32 operands")
+        rc = L.b200vq_gemm_f16(_p(a), lda, a_major, _p(b), ldb, b_major, _p(out), N, int(out_half), M, N, K, splits, M * N,
+                               _p(bias), _p(res), ldres, res_row_mod, _p(aux), ldaux, _p(part), act, int(round_out), _p(alpha),
+                               cta_group, bn, _stream())
+        _lib.check(rc, "gemm_f16")
+    elif a_lo is not None:
+        _req(a_lo, "a_lo"); _req(b_lo, "b_lo")
+        if out_half or alpha is not None:
+            raise RuntimeError("b200vq: fp16 output / alpha belong to the fp16 GEMM")
+        rc = L.b200vq_gemm_3xtf32(_p(a), _p(a_lo), lda, a_major, _p(b), _p(b_lo), ldb, b_major, _p(out), N, M, N, K, splits,
+                                  M * N, _p(bias), _p(res), ldres, res_row_mod, _p(aux), ldaux, _p(part), act, cta_group, bn,
+                                  _stream())
+        _lib.check(rc, "gemm_3xtf32")
+    else:
+        if out_half or alpha is not None:
+            raise RuntimeError("b200vq: fp16 output / alpha belong to the fp16 GEMM")
+        rc = L.b200vq_gemm_tf32(_p(a), lda, a_major, _p(b), ldb, b_major, _p(out), N, M, N, K, splits, M * N,
+                                _p(bias), _p(res), ldres, res_row_mod, _p(aux), ldaux, _p(part), act, int(round_out),
+                                cta_group, bn, _stream())
+        _lib.check(rc, "gemm_tf32")
     if want_colsum:
         return out, colsum(part)
     return out
 
 
-def splitk_reduce(part: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    _req(part, "part")
+def splitk_reduce(part: Tensor, out: Optional[Tensor] = None, alpha: Optional[Tensor] = None) -> Tensor:
+    _req(part, "part"); _req(alpha, "alpha")
     splits = part.shape[0]
     n = part[0].numel()
     if out is None:
         out = torch.empty(part.shape[1:], device=part.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_splitk_reduce(_p(part), splits, n, n, _p(out), _stream()), "splitk_reduce")
+    _lib.check(_lib.lib().b200vq_splitk_reduce(_p(part), splits, n, n, _p(alpha), _p(out), _stream()), "splitk_reduce")
     return out
 
 
-def pick_splits(k_total: int, out_rows: int, out_cols: int, sms: int = 148) -> int:
+def pick_splits(k_total: int, out_rows: int, out_cols: int, sms: int = 148, k_atom: int = 32) -> int:
     """split count for a wgrad GEMM: enough (tile x split) work items to fill the SMs twice,
-    each split contracting a multiple of 32."""
+    each split contracting a multiple of one k-block (32 fp32 / 64 fp16 elements)."""
     tiles = -(-out_rows // 128) * -(-out_cols // 256)
     want = max(1, (2 * sms + tiles - 1) // tiles)
     s = 1
-    while s * 2 <= want and k_total % (s * 2 * 32) == 0 and k_total // (s * 2) >= 256:
+    while s * 2 <= want and k_total % (s * 2 * k_atom) == 0 and k_total // (s * 2) >= 256:
         s *= 2
     return s
 
 
+# ------------------------------------------------------------------------ operand preparation
+def split_tf32_lo(x: Tensor) -> Tensor:
+    """x - trunc_tf32(x): the residue the 3xTF32 product feeds back in"""
+    _req(x, "x")
+    lo = torch.empty_like(x)
+    _lib.check(_lib.lib().b200vq_split_tf32_lo(_p(x), _p(lo), x.numel(), _stream()), "split_tf32_lo")
+    return lo
+
+
+def to_half(x: Tensor, scale: Optional[Tensor] = None) -> Tensor:
+    """fp16(x * scale), saturating; scale is a device scalar (element 0 of a grad_scale() pair) or None"""
+    _req(x, "x"); _req(scale, "scale")
+    out = torch.empty(x.shape, device=x.device, dtype=_HALF)
+    _lib.check(_lib.lib().b200vq_to_half(_p(x), _p(out), x.numel(), _p(scale), _stream()), "to_half")
+    return out
+
+
+GRAD_TARGET_LOG2 = 6   # max|g| * S ~ 2^6: ~2^10 of headroom to fp16's 65504, full precision down to 2^-20 of max|g|
+
+
+def grad_scale(g: Tensor, target_log2: int = GRAD_TARGET_LOG2) -> Tensor:
+    """-> device tensor [S, 1/S], S the power of two that puts max|g| at ~2^target_log2 (no host sync)"""
+    _req(g, "g")
+    L = _lib.lib()
+    ws_bytes = L.b200vq_grad_scale_workspace_bytes()
+    ws = torch.empty(ws_bytes // 4, device=g.device, dtype=torch.float32)
+    scale2 = torch.empty(2, device=g.device, dtype=torch.float32)
+    _lib.check(L.b200vq_grad_scale(_p(g), g.numel(), int(target_log2), _p(scale2), _p(ws), ws_bytes, _stream()), "grad_scale")
+    return scale2
+
+
 # ------------------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, round_out: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, round_out: bool, out_half: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
     D = x.shape[-1]
     M = x.numel() // D
-    y = torch.empty_like(x)
+    y = torch.empty(x.shape, device=x.device, dtype=_HALF if out_half else torch.float32)
     mean = torch.empty(M, device=x.device, dtype=torch.float32)
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D,
-                                               int(round_out), _stream()), "layernorm_fwd")
+    _lib.check(_lib.lib().b200vq_layernorm_fwd(_p(x), _p(gamma), _p(beta), None if out_half else _p(y), _p(y) if out_half else None,
+                                               _p(mean), _p(rstd), M, D, int(round_out), _stream()), "layernorm_fwd")
     return y, mean, rstd
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
-                  round_out: bool = False, want_colsum: bool = False):
-    """-> (dx, dgamma, dbeta) or, with want_colsum, (dx, dgamma, dbeta, colsum(dx))"""
-    _req(dy, "dy"); _req(x, "x"); _req(dres, "dres")
+                  round_out: bool = False, want_colsum: bool = False, half_scale: Optional[Tensor] = None):
+    """-> (dx, dgamma, dbeta) or, with want_colsum, (dx, dgamma, dbeta, colsum(dx)); with half_scale (device
+    scalar) a further element: the fp16 copy fp16(dx * scale)"""
+    _req(dy, "dy"); _req(x, "x"); _req(dres, "dres"); _req(half_scale, "half_scale")
     D = x.shape[-1]
     M = x.numel() // D
     L = _lib.lib()
     ws_bytes = L.b200vq_layernorm_bwd_workspace_bytes(D)
     ws = torch.empty(ws_bytes // 4, device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
+    dx16 = torch.empty(x.shape, device=x.device, dtype=_HALF) if half_scale is not None else None
     dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
     dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
     dxsum = torch.empty(D, device=x.device, dtype=torch.float32) if want_colsum else None
-    _lib.check(L.b200vq_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma),
-                                      _p(dbeta), _p(dxsum), M, D, int(round_out), _p(ws), ws_bytes, _stream()), "layernorm_bwd")
-    if want_colsum:
-        return dx, dgamma, dbeta, dxsum
-    return dx, dgamma, dbeta
+    _lib.check(L.b200vq_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(half_scale),
+                                      _p(dgamma), _p(dbeta), _p(dxsum), M, D, int(round_out), _p(ws), ws_bytes, _stream()),
+               "layernorm_bwd")
+    res = (dx, dgamma, dbeta) + ((dxsum,) if want_colsum else ())
+    return res + ((dx16,) if half_scale is not None else ())
 
 
 # ------------------------------------------------------------------------------------- attention
-def attention_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float, round_out: bool) -> Tuple[Tensor, Tensor]:
+def attention_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float, round_out: bool,
+                  out_half: bool = False) -> Tuple[Tensor, Tensor]:
     _req(qkv, "qkv")
-    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=torch.float32)
+    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=_HALF if out_half else torch.float32)
     lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_attention_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, dh, scale, int(round_out),
+    _lib.check(_lib.lib().b200vq_attention_fwd(_p(qkv), _p(out), int(out_half), _p(lse), B, N, heads, dh, scale, int(round_out),
                                                _stream()), "attention_fwd")
     return out, lse
 
 
 def attention_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, heads: int, dh: int,
-                  scale: float, round_out: bool) -> Tensor:
+                  scale: float, round_out: bool, half_scale: Optional[Tensor] = None) -> Tensor:
+    """dqkv (fp32; or, with half_scale, fp16(dqkv * scale)).  `out` is the forward's output in whichever dtype it stored."""
+    _req(qkv, "qkv"); _req(out, "out", out.dtype if out.dtype == _HALF else torch.float32); _req(lse, "lse"); _req(dout, "dout")
+    _req(half_scale, "half_scale")
+    dq_half = half_scale is not None
+    dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=_HALF if dq_half else torch.float32)
+    delta = torch.empty_like(lse)
+    _lib.check(_lib.lib().b200vq_attention_bwd(_p(qkv), _p(out), int(out.dtype == _HALF), _p(lse), _p(dout), _p(dqkv), int(dq_half),
+                                               _p(half_scale), _p(delta), B, N, heads, dh, scale, int(round_out), _stream()),
+               "attention_bwd")
+    return dqkv
+
+
+def attention_exact_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float) -> Tuple[Tensor, Tensor]:
+    _req(qkv, "qkv")
+    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_attention_exact_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, dh, scale, _stream()),
+               "attention_exact_fwd")
+    return out, lse
+
+
+def attention_exact_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, heads: int, dh: int,
+                        scale: float) -> Tensor:
     _req(qkv, "qkv"); _req(out, "out"); _req(lse, "lse"); _req(dout, "dout")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    _lib.check(_lib.lib().b200vq_attention_bwd(_p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(delta), B, N, heads, dh,
-                                               scale, int(round_out), _stream()), "attention_bwd")
+    _lib.check(_lib.lib().b200vq_attention_exact_bwd(_p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(delta), B, N, heads, dh,
+                                                     scale, _stream()), "attention_exact_bwd")
     return dqkv
 
 
 # ------------------------------------------------------------------------------------- quantiser
-def vq_fwd(z: Tensor, E: Tensor, depth: int, beta: float) -> Tuple[Tensor, Tensor, Tensor]:
+def vq_fwd(z: Tensor, E: Tensor, depth: int, beta: float, use_norm: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
     """z [..., D], E [K, D] -> (straight-through value like z, loss scalar, idx int64 [M, depth])"""
     _req(z, "z"); _req(E, "embedding.weight")
     K, D = E.shape
@@ -149,13 +251,13 @@ def vq_fwd(z: Tensor, E: Tensor, depth: int, beta: float) -> Tuple[Tensor, Tenso
     out = torch.empty_like(z)
     idx = torch.empty(M, depth, device=z.device, dtype=torch.int64)
     loss = torch.empty((), device=z.device, dtype=torch.float32)
-    _lib.check(L.b200vq_vq_fwd(_p(z), _p(E), _p(out), _p(idx), _p(loss), M, K, D, depth, float(beta), _p(ws), ws_bytes,
-                               _stream()), "vq_fwd")
+    _lib.check(L.b200vq_vq_fwd(_p(z), _p(E), _p(out), _p(idx), _p(loss), M, K, D, depth, float(beta), int(use_norm), _p(ws),
+                               ws_bytes, _stream()), "vq_fwd")
     return out, loss, idx
 
 
 def vq_bwd(z: Tensor, E: Tensor, idx: Tensor, g_out: Optional[Tensor], g_loss: Optional[Tensor], residual: bool,
-           beta: float) -> Tuple[Tensor, Tensor]:
+           beta: float, use_norm: bool = True) -> Tuple[Tensor, Tensor]:
     _req(z, "z"); _req(E, "embedding.weight"); _req(idx, "idx", torch.int64); _req(g_out, "g_out"); _req(g_loss, "g_loss")
     K, D = E.shape
     M = z.numel() // D
@@ -163,16 +265,16 @@ def vq_bwd(z: Tensor, E: Tensor, idx: Tensor, g_out: Optional[Tensor], g_loss: O
     gz = torch.empty_like(z)
     gE = torch.empty_like(E)
     _lib.check(_lib.lib().b200vq_vq_bwd(_p(z), _p(E), _p(idx), _p(g_out), _p(g_loss), _p(gz), _p(gE), M, K, D, depth,
-                                        int(residual), float(beta), _stream()), "vq_bwd")
+                                        int(residual), float(beta), int(use_norm), _stream()), "vq_bwd")
     return gz, gE
 
 
-def vq_embed(E: Tensor, codes: Tensor, depth: int) -> Tensor:
+def vq_embed(E: Tensor, codes: Tensor, depth: int, use_norm: bool = True) -> Tensor:
     _req(E, "embedding.weight"); _req(codes, "codes", torch.int64)
     K, D = E.shape
     M = codes.numel() // depth
     out = torch.empty(M, D, device=E.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_vq_embed(_p(E), _p(codes), _p(out), M, K, D, depth, _stream()), "vq_embed")
+    _lib.check(_lib.lib().b200vq_vq_embed(_p(E), _p(codes), _p(out), M, K, D, depth, int(use_norm), _stream()), "vq_embed")
     return out
 
 

@@ -41,9 +41,6 @@ class VectorQuantizer(BaseQuantizer):
                  use_residual: bool = False, num_quantizers: Optional[int] = None, **kwargs) -> None:
         super().__init__(embed_dim, n_embed, True, use_norm, use_residual, num_quantizers)
         self.beta = beta
-        if not use_norm:
-            raise NotImplementedError("b200vq: only the l2-normalised quantiser (use_norm=True, every shipped "
-                                      "config) is built; refusing to fall back to a PyTorch path")
         if use_residual and not num_quantizers:
             raise ValueError("use_residual=True needs num_quantizers")
 
@@ -54,7 +51,7 @@ class VectorQuantizer(BaseQuantizer):
     def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         zc = z.contiguous()
         out, loss, idx = Fn.VectorQuantizeFn.apply(zc.view(-1, self.embed_dim), self.embedding.weight, self.depth,
-                                                   float(self.beta), bool(self.use_residual))
+                                                   float(self.beta), bool(self.use_residual), bool(self.use_norm))
         out = out.view_as(zc)
         idx = idx.view(*z.shape[:-1], self.depth) if self.use_residual else idx.view(*z.shape[:-1])
         return out, loss, idx
@@ -63,12 +60,13 @@ class VectorQuantizer(BaseQuantizer):
         """single-depth lookup (quantizers.py:74-92): (normalised code, loss, indices).  Inference helper:
         the returned code carries no autograd graph; training goes through forward()."""
         zc = z.detach().contiguous().view(-1, self.embed_dim)
-        _, loss, idx = ops.vq_fwd(zc, self.embedding.weight.detach(), 1, float(self.beta))
-        q = ops.vq_embed(self.embedding.weight.detach(), idx, 1).view_as(z)
+        _, loss, idx = ops.vq_fwd(zc, self.embedding.weight.detach(), 1, float(self.beta), bool(self.use_norm))
+        q = ops.vq_embed(self.embedding.weight.detach(), idx, 1, bool(self.use_norm)).view_as(z)
         return q, loss, idx.view(*z.shape[:-1])
 
     def embed_codes(self, code: torch.Tensor) -> torch.Tensor:
         """decode_codes fast path (vitvqgan.py:81-86 in one kernel): sum_t normalize(E[code[..., t]])"""
         depth = self.depth
         lead = code.shape[:-1] if self.use_residual else code.shape
-        return ops.vq_embed(self.embedding.weight.detach(), code.contiguous().view(-1, depth), depth).view(*lead, self.embed_dim)
+        return ops.vq_embed(self.embedding.weight.detach(), code.contiguous().view(-1, depth), depth,
+                            bool(self.use_norm)).view(*lead, self.embed_dim)

@@ -17,7 +17,8 @@
  *   - matrices are row-major with an explicit leading dimension in elements;
  *   - `round_out != 0` stores values rounded to tf32 (round-to-nearest, fp32 container) because
  *     the tensor is only ever consumed as a tcgen05 kind::tf32 operand, which would otherwise
- *     truncate the low 13 mantissa bits.
+ *     truncate the low 13 mantissa bits;
+ *   - fp16 buffers (void*) are plain IEEE binary16 arrays; they only ever hold GEMM operands.
  */
 #ifndef B200VQ_H_
 #define B200VQ_H_
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200VQ_VERSION 100 /* 0.1.0 */
+#define B200VQ_VERSION 200 /* 0.2.0 */
 
 int b200vq_version(void);
 const char* b200vq_last_error(void);
@@ -37,61 +38,97 @@ const char* b200vq_last_error(void);
 const char* b200vq_arch(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 long long b200vq_launch_count(void);
+/* cap the grid of the persistent (one CTA per SM) GEMM / attention kernels at n CTAs, 0 = no cap.  Leaves SMs to a
+ * concurrently running NCCL all-reduce (reference main.py:54-57 strategy="ddp").  Also read once from the environment
+ * variable B200VQ_SM_LIMIT. */
+int b200vq_set_sm_limit(int n);
 
-/* ---- GEMM: C[M,N] = epi( A . B^T ) on tcgen05 tensor cores, tf32 in / fp32 accumulate ---------
+/* ---- GEMM: C[M,N] = epi( alpha * A . B^T ) on tcgen05 tensor cores, fp32 accumulate ------------------
  * Replaces nn.Linear / Conv2d(k=s) / ConvTranspose2d(k=s) forward, dgrad and wgrad:
- *   layers.py:99-101 (FeedForward), :118,:120 (to_qkv, to_out), :169 (patch embed), :204 (to_pixel).
+ *   layers.py:99-101 (FeedForward), :118,:120 (to_qkv, to_out), :169 (patch embed), :204 (to_pixel),
+ *   vitvqgan.py:38-39 (pre_quant / post_quant).
  * a_major/b_major: 0 = operand stored [rows, K] (K contiguous); 1 = stored [K_total, rows]
  * (rows contiguous).  splits > 1 contracts K_total = K*splits in `splits` slices and writes
  * slice z to C + z*c_split_stride (reduce with b200vq_splitk_reduce).
- * Epilogue, in this order: + bias[N]; act (0 none, 1 tanh -- layers.py:100);
+ * Epilogue, in this order: * alpha; + bias[N]; act (0 none, 1 tanh -- layers.py:100);
  * * (1 - aux^2) (tanh backward); + res[row % res_row_mod or row] (residual add layers.py:147-148
- * or positional table :179,:210); tf32 rounding.
+ * or positional table :179,:210); tf32 rounding / fp16 conversion.
  * colsum_part (nullable, [ceil(M/32)][N], splits must be 1): receives the column sums of every 32-row group of
  * the stored C -- summed over the groups (b200vq_colsum) they are the bias gradient of the Linear whose
  * pre-activation gradient this GEMM produced (net.0, layers.py:99), without another pass over C.
- * cta_group: 1 = one CTA per 128 x bn tile, 2 = CTA pair per 256 x bn tile; bn in {0=auto,64,128,192,256}. */
+ * cta_group: 1 = one CTA per 128 x bn tile, 2 = CTA pair per 256 x bn tile; bn in {0=auto,64,128,192,256}.
+ *
+ * Three operand flavours:
+ *   gemm_tf32   A, B fp32, kind::tf32 (10-bit mantissa; the hardware truncates, so producers round to nearest).
+ *   gemm_3xtf32 A, B fp32 plus their truncation residues A_lo, B_lo (b200vq_split_tf32_lo): the
+ *               error-compensated product A_lo.B + A.B_lo + A.B -- fp32-grade, used by precision="parity".
+ *   gemm_f16    A, B fp16 (kind::f16: the same 11-bit significand as tf32 at twice the tensor rate and half the
+ *               operand bytes); C fp32, or fp16 when out_half (then aux is fp16 too; no residual / split-K).
+ *               alpha (device scalar, nullable) undoes the power-of-two scale fp16 gradient operands carry. */
 int b200vq_gemm_tf32(const float* A, long long lda, int a_major, const float* B, long long ldb, int b_major,
                      float* C, long long ldc, int M, int N, int K, int splits, long long c_split_stride,
                      const float* bias, const float* res, long long ldres, int res_row_mod,
                      const float* aux, long long ldaux, float* colsum_part, int act, int round_out, int cta_group,
                      int bn, void* stream);
-int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, float* out, void* stream);
+int b200vq_gemm_3xtf32(const float* A, const float* A_lo, long long lda, int a_major, const float* B, const float* B_lo,
+                       long long ldb, int b_major, float* C, long long ldc, int M, int N, int K, int splits,
+                       long long c_split_stride, const float* bias, const float* res, long long ldres, int res_row_mod,
+                       const float* aux, long long ldaux, float* colsum_part, int act, int cta_group, int bn, void* stream);
+int b200vq_gemm_f16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* C,
+                    long long ldc, int out_half, int M, int N, int K, int splits, long long c_split_stride,
+                    const float* bias, const float* res, long long ldres, int res_row_mod, const void* aux,
+                    long long ldaux, float* colsum_part, int act, int round_out, const float* alpha, int cta_group,
+                    int bn, void* stream);
+/* out = alpha * sum_z part[z] (alpha: device scalar or NULL) */
+int b200vq_splitk_reduce(const float* part, int splits, long long n, long long split_stride, const float* alpha,
+                         float* out, void* stream);
 
-/* ---- LayerNorm (nn.LayerNorm(dim), eps 1e-5: layers.py:88,143) ---------------------------------*/
-int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                         int M, int D, int round_out, void* stream);
+/* ---- LayerNorm (nn.LayerNorm(dim), eps 1e-5: layers.py:88,143) ---------------------------------
+ * y (fp32, optionally tf32-rounded) and/or y16 (fp16) receive the normalised rows; either may be NULL. */
+int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y16, float* mean,
+                         float* rstd, int M, int D, int round_out, void* stream);
 size_t b200vq_layernorm_bwd_workspace_bytes(int D);
 /* dx = LN'(dy) (+ dres, the skip-connection gradient of layers.py:147-148).  dxsum (nullable, [D]) receives the
  * column sums of dx: dx is also the gradient at the bias of the Linear that wrote this residual stream
- * (to_out layers.py:118, net.2 layers.py:101), so that bias gradient costs no extra pass over dx. */
+ * (to_out layers.py:118, net.2 layers.py:101), so that bias gradient costs no extra pass over dx.
+ * dx16 (nullable): fp16 copy of dx multiplied by *dx16_scale, the operand of the next block's fp16 GEMMs. */
 int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
-                         int round_out, void* workspace, size_t ws_bytes, void* stream);
+                         const float* dres, float* dx, void* dx16, const float* dx16_scale, float* dgamma,
+                         float* dbeta, float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes,
+                         void* stream);
 
 /* ---- attention core (layers.py:124-130): softmax(q k^T * scale) v, no mask -----------------------
  * qkv is the [B*N, 3*heads*dh] output of to_qkv (q | k | v thirds, head h at columns h*dh);
- * out is [B*N, heads*dh]; lse [B*heads*N] holds log-sum-exp of the scaled scores (saved for
- * backward instead of the [B,h,N,N] probabilities the reference keeps).  dh must be 64 or 32. */
-int b200vq_attention_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
-                         int round_out, void* stream);
-/* dqkv [B*N, 3*heads*dh] from dout; delta [B*heads*N] is scratch (rowsum(dout*out)) */
-int b200vq_attention_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
-                         float* delta, int B, int N, int heads, int dh, float scale, int round_out, void* stream);
+ * out is [B*N, heads*dh] (fp32, or fp16 when out_half); lse [B*heads*N] holds log-sum-exp of the scaled scores
+ * (saved for backward instead of the [B,h,N,N] probabilities the reference keeps).  dh must be 64 or 32. */
+int b200vq_attention_fwd(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, int dh,
+                         float scale, int round_out, void* stream);
+/* dqkv [B*N, 3*heads*dh] from dout (fp32); `out` as the forward stored it; delta [B*heads*N] is scratch
+ * (rowsum(dout*out)).  dqkv_half: store fp16, multiplied by *dqkv_scale (nullable). */
+int b200vq_attention_bwd(const float* qkv, const void* out, int out_half, const float* lse, const float* dout,
+                         void* dqkv, int dqkv_half, const float* dqkv_scale, float* delta, int B, int N, int heads,
+                         int dh, float scale, int round_out, void* stream);
+/* the same contract with every product in error-compensated 3xTF32 (fp32-grade; precision="parity") */
+int b200vq_attention_exact_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
+                               void* stream);
+int b200vq_attention_exact_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                               float* delta, int B, int N, int heads, int dh, float scale, void* stream);
 
 /* ---- vector quantiser (quantizers.py:38-92) ------------------------------------------------------
  * z [M,D], codebook E [K,D] (un-normalised nn.Embedding weight); out [M,D] = straight-through
  * value z + (z_q - z); idx int64 [M, depth]; loss: device scalar.  depth = 1 for the plain
- * quantiser, num_quantizers for use_residual=True. */
+ * quantiser, num_quantizers for use_residual=True.  use_norm: quantizers.py:24 (1 = l2-normalise). */
 size_t b200vq_vq_workspace_bytes(int M, int K, int depth);
 int b200vq_vq_fwd(const float* z, const float* E, float* out, long long* idx, float* loss, int M, int K, int D,
-                  int depth, float beta, void* workspace, size_t ws_bytes, void* stream);
+                  int depth, float beta, int use_norm, void* workspace, size_t ws_bytes, void* stream);
 /* g_out [M,D] or NULL, g_loss device scalar or NULL; gz [M,D] written, gE [K,D] zero-filled then
  * accumulated (nn.Embedding dense backward). */
 int b200vq_vq_bwd(const float* z, const float* E, const long long* idx, const float* g_out, const float* g_loss,
-                  float* gz, float* gE, int M, int K, int D, int depth, int residual, float beta, void* stream);
-/* decode_codes (vitvqgan.py:81-86): out[m] = sum_t normalize(E[codes[m,t]]) */
-int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, int K, int D, int depth, void* stream);
+                  float* gz, float* gE, int M, int K, int D, int depth, int residual, float beta, int use_norm,
+                  void* stream);
+/* decode_codes (vitvqgan.py:81-86): out[m] = sum_t norm(E[codes[m,t]]) */
+int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, int K, int D, int depth, int use_norm,
+                    void* stream);
 
 /* ---- re-layout / reductions ------------------------------------------------------------------------*/
 /* [B,C,H,W] -> [B*(H/p)*(W/p), C*p*p], patch vector ordered (c,ph,pw) (layers.py:168-171) */
@@ -106,6 +143,18 @@ int b200vq_round_tf32(const float* in, float* out, long long n, void* stream);
 
 /* out[m,:] = x[m,:] + table[m % R,:]  (token + de_pos_embedding, layers.py:210) */
 int b200vq_add_rows_mod(const float* x, const float* table, float* out, long long M, int D, int R, void* stream);
+
+
+/* ---- operand preparation for the 3xTF32 and fp16 data paths --------------------------------------*/
+/* lo = in - trunc_tf32(in): the bits kind::tf32 drops (exact in fp32) */
+int b200vq_split_tf32_lo(const float* in, float* lo, long long n, void* stream);
+/* out16 = fp16(in * *scale), saturating at +-65504 (scale: device scalar or NULL) */
+int b200vq_to_half(const float* in, void* out16, long long n, const float* scale, void* stream);
+/* scale2 = {S, 1/S}, S = 2^(target_log2 - ceil(log2(max|g|))): the power-of-two gradient scale of one backward
+ * segment, chosen on the device from the incoming gradient (no host synchronisation) */
+size_t b200vq_grad_scale_workspace_bytes(void);
+int b200vq_grad_scale(const float* g, long long n, int target_log2, float* scale2, void* workspace, size_t ws_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

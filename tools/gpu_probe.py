@@ -257,7 +257,7 @@ def _load_modules(cfg, sd, device="cuda"):
     enc = etb.ViTEncoder(cfg["image_size"], cfg["patch_size"], **e)
     dec = etb.ViTDecoder(cfg["image_size"], cfg["patch_size"], **d)
     vq = etb.VectorQuantizer(**q)
-    pre = torch.nn.Linear(e["dim"], q["embed_dim"]); post = torch.nn.Linear(q["embed_dim"], d["dim"])
+    pre = etb.QuantLinear(e["dim"], q["embed_dim"]); post = etb.QuantLinear(q["embed_dim"], d["dim"])
     for pfx, m in (("encoder.", enc), ("decoder.", dec), ("quantizer.", vq), ("pre_quant.", pre), ("post_quant.", post)):
         m.load_state_dict({k[len(pfx):]: v for k, v in sd.items() if k.startswith(pfx)}, strict=True)
         m.to(device)
@@ -333,7 +333,6 @@ def g_model_small():
         worst.sort(reverse=True)
         print("   worst grad rel-l2:", [(f"{e:.2e}", k) for e, k in worst[:5]])
         del mods
-        etb.functional.clear_shadow_cache()
         torch.cuda.empty_cache()
 
 
@@ -395,7 +394,75 @@ def g_precision():
         print(f"{name}: enc relmax {relerr(h.double(), h64):.2e} rel-l2 {((h.double()-h64).norm()/h64.norm()).item():.2e} | z relmax {relerr(z.double(), z64):.2e} | "
               f"idx agree {(idx == idx64).float().mean().item():.5f} | dec-only (same codes) relmax {relerr(rec.double(), rec64):.2e} rel-l2 {((rec.double()-rec64).norm()/rec64.norm()).item():.2e}", flush=True)
         del mods
-        etb.functional.clear_shadow_cache(); torch.cuda.empty_cache()
+        torch.cuda.empty_cache()
+
+
+def g_f16perf():
+    """GEMM throughput of the two operand kinds at the config-2 shapes (M = 131072 tokens)"""
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    M = 131072
+    H = torch.float16
+    alpha = torch.tensor([0.5], device="cuda")
+    shapes = [("to_qkv fwd", 2304, 768, {}), ("to_out fwd", 768, 768, {}), ("mlp1 fwd", 3072, 768, {}), ("mlp2 fwd", 768, 3072, {})]
+    for nm, N, K, _ in shapes:
+        for kind in ("tf32", "f16"):
+            dt = H if kind == "f16" else torch.float32
+            a = torch.randn(M, K, device="cuda").to(dt); b = torch.randn(N, K, device="cuda").to(dt)
+            ms = time_ms(lambda: ops.gemm(a, b, M, N, K, cta_group=2), iters=5, warm=2)
+            line = f"{nm:12s} N={N:5d} K={K:5d} {kind:5s} out32: {ms:.3f} ms {2*M*N*K/ms/1e9:7.1f} TFLOP/s"
+            if kind == "f16":
+                bias = torch.randn(N, device="cuda")
+                ms2 = time_ms(lambda: ops.gemm(a, b, M, N, K, bias=bias, act=1, out_half=True, cta_group=2), iters=5, warm=2)
+                line += f" | out16+tanh: {ms2:.3f} ms {2*M*N*K/ms2/1e9:7.1f}"
+            print(line, flush=True)
+            del a, b
+    # dgrad (B MN-major) and wgrad (both MN-major, split-K)
+    for nm, N, K in [("mlp2 dgrad", 3072, 768), ("mlp1 dgrad", 768, 3072), ("qkv dgrad", 768, 2304)]:
+        for kind in ("tf32", "f16"):
+            dt = H if kind == "f16" else torch.float32
+            a = torch.randn(M, K, device="cuda").to(dt); b = torch.randn(K, N, device="cuda").to(dt)
+            ms = time_ms(lambda: ops.gemm(a, b, M, N, K, b_major=1, cta_group=2), iters=5, warm=2)
+            print(f"{nm:12s} N={N:5d} K={K:5d} {kind:5s}: {ms:.3f} ms {2*M*N*K/ms/1e9:7.1f} TFLOP/s", flush=True)
+            del a, b
+    for nm, R, C in [("mlp wgrad", 768, 3072), ("qkv wgrad", 2304, 768), ("out wgrad", 768, 768)]:
+        for kind in ("tf32", "f16"):
+            dt = H if kind == "f16" else torch.float32
+            dy = torch.randn(M, R, device="cuda").to(dt); x = torch.randn(M, C, device="cuda").to(dt)
+            splits = ops.pick_splits(M, R, C, k_atom=64 if kind == "f16" else 32)
+            def run():
+                part = ops.gemm(dy, x, R, C, M // splits, a_major=1, b_major=1, splits=splits, cta_group=2)
+                return ops.splitk_reduce(part, alpha=alpha) if splits > 1 else part
+            ms = time_ms(run, iters=5, warm=2)
+            print(f"{nm:12s} [{R}x{C}] splits={splits} {kind:5s}: {ms:.3f} ms {2*M*R*C/ms/1e9:7.1f} TFLOP/s", flush=True)
+            del dy, x
+
+
+def g_modes():
+    """fwd+bwd step time of the hot path per precision mode (base, B from argv, default 32)"""
+    import sys
+    import torch
+    from oracle import vitvq_oracle as O
+    import enhancing_transformers_b200 as etb
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+    cfg = O.CONFIGS["base"]
+    sd = O.init_vitvq_sd(cfg, seed=0)
+    mods = _load_modules(cfg, sd)
+    params = [p for m in mods for p in m.parameters()]
+    img = torch.rand(B, 3, 256, 256, device="cuda")
+    for mode in ("tf32", "fp16") + (("parity",) if B <= 8 else ()):
+        etb.set_precision(mode)
+
+        def step():
+            for p in params:
+                p.grad = None
+            loss = _step(mods, img)[0]
+            loss.backward()
+            return loss
+        ms = time_ms(step, iters=3, warm=2)
+        print(f"mode {mode:6s} base B={B}: {ms:.1f} ms/step  {B/ms*1e3:.1f} img/s  loss {step().item():.6f} "
+              f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 
 
 def g_attn_trace():
