@@ -4,12 +4,12 @@
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29500 bench.py --gpus 8 --steps 5 --warmup 3
-    python bench.py --impl reference --steps 2 --warmup 1      # the CPU arm (oracle port)
+    python bench.py --impl reference --steps 3 --warmup 1      # the CPU arm (reference modules / oracle port)
 
 One "step" = x -> ViTEncoder -> pre_quant -> VectorQuantizer -> post_quant -> ViTDecoder ->
 loss = mean((rec-x)^2) + qloss -> backward, fp32 parameters, no optimizer step (SURVEY.md
 section 8d).  Workload: imagenet_vitvq_base.yaml shapes, synthetic 256x256 images, batch 128
-per GPU (BASELINE.json configs[1]); weak scaling, gradients all-reduced by NCCL (DDP).
+per GPU (BASELINE.json configs[1]); weak scaling, gradients all-reduced over NCCL.
 
 Prints ONE JSON line on rank 0 (see DESIGN.md 'Measurement' for every key).
 """
@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (256x256) ViT-VQGAN fwd+bwd"
 UNIT = "images/s"
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FMA lanes x 2 FLOP x 1.965 GHz = 74.5
 
 
 def load_peaks():
@@ -71,74 +72,194 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "power_w_max": pw}
 
 
-def oracle_step(cfg_name, batch, threads):
-    """one fwd+bwd of the CPU oracle (the port of the reference's PyTorch path); returns seconds"""
-    import torch
-    from oracle import vitvq_oracle as O
-    torch.set_num_threads(threads)
-    cfg = O.CONFIGS[cfg_name]
-    sd = O.init_vitvq_sd(cfg, seed=0)
-    sd = {k: v.requires_grad_(v.is_floating_point() and "pos_embedding" not in k) for k, v in sd.items()}
-    img = torch.rand(batch, 3, cfg["image_size"], cfg["image_size"], generator=torch.Generator().manual_seed(0))
+# ------------------------------------------------------------------------------------------------
+# the reference's own PyTorch path (CPU arm and eager-GPU arm)
+# ------------------------------------------------------------------------------------------------
+def reference_modules():
+    """the reference's layers.py / quantizers.py, vendored unmodified into oracle/_ref by oracle/build_ref.py
+    (git-ignored; they travel to the GPU box with the snapshot).  None if absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref", "enhancing_ref")
+    if not (os.path.exists(os.path.join(ref_dir, "layers.py")) and os.path.exists(os.path.join(ref_dir, "quantizers.py"))):
+        return None
+    import importlib.util
+    import numpy as np
+    if not hasattr(np, "float"):
+        np.float = float                      # layers.py:57 uses the alias numpy removed in 1.24 (harness-side shim)
+    mods = {}
+    for name in ("layers", "quantizers"):
+        spec = importlib.util.spec_from_file_location(f"enhancing_ref.{name}", os.path.join(ref_dir, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods
 
-    def step():
-        for v in sd.values():
-            v.grad = None
-        t0 = time.perf_counter()
-        loss, _, _ = O.vitvq_loss(sd, img, cfg)
+
+class RefHotPath:
+    """encoder -> pre_quant -> quantizer -> post_quant -> decoder -> loss with the REFERENCE's own nn.Modules
+    (kind "reference"), or with the oracle port when oracle/_ref is absent (kind "port")"""
+
+    def __init__(self, cfg_name, device, seed=0):
+        import torch
+        from oracle import vitvq_oracle as O
+        self.torch, self.O, self.device = torch, O, device
+        self.cfg = cfg = O.CONFIGS[cfg_name]
+        ref = reference_modules()
+        sd = O.init_vitvq_sd(cfg, seed=seed)
+        if ref is not None:
+            self.kind = "reference"
+            e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
+            self.mods = dict(encoder=ref["layers"].ViTEncoder(cfg["image_size"], cfg["patch_size"], **e),
+                             decoder=ref["layers"].ViTDecoder(cfg["image_size"], cfg["patch_size"], **d),
+                             quantizer=ref["quantizers"].VectorQuantizer(**q),
+                             pre_quant=torch.nn.Linear(e["dim"], q["embed_dim"]), post_quant=torch.nn.Linear(q["embed_dim"], d["dim"]))
+            for name, m in self.mods.items():
+                m.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=True)
+                m.to(device)
+            self.params = [p for m in self.mods.values() for p in m.parameters()]
+        else:
+            self.kind = "port"
+            self.sd = {k: v.to(device).requires_grad_(v.is_floating_point() and "pos_embedding" not in k) for k, v in sd.items()}
+            self.params = list(self.sd.values())
+
+    def step(self, img):
+        for p in self.params:
+            p.grad = None
+        if self.kind == "reference":
+            m = self.mods
+            quant, qloss, _ = m["quantizer"](m["pre_quant"](m["encoder"](img)))
+            rec = m["decoder"](m["post_quant"](quant))
+            loss = ((rec - img) ** 2).mean() + qloss
+        else:
+            loss, _, _ = self.O.vitvq_loss(self.sd, img, self.cfg)
         loss.backward()
-        return time.perf_counter() - t0
-    return step
+        return loss
 
 
-def pick_cpu_threads(cfg_name):
-    """The reference arm may use every host thread, but on the 2-socket / 128-thread GPU hosts torch's
-    intra-op pool collapses when oversubscribed (measured: base B=4 takes 94 s with 128 threads, 4 s
-    with 32).  Calibrate on one image and keep the fastest of {16, 32, 64, all}."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in (16, 32, 64, ncpu) if t <= ncpu} or {ncpu})
-    if len(cands) == 1:
-        return cands[0]
-    best, best_t = cands[0], float("inf")
-    for t in cands:
-        step = oracle_step(cfg_name, 1, t)
-        sec = step()
-        if sec < best_t:
-            best, best_t = t, sec
-        if sec > 4 * best_t:      # clearly past the knee: do not spend a minute on the oversubscribed setting
-            break
-    return best
+def cpu_threads():
+    """torch's intra-op pool collapses when oversubscribed on the 2-socket / 128-thread GPU hosts (measured round 1:
+    base B=4 takes 94 s with 128 threads, 4 s with 32): a fixed 32 threads (or every core of a smaller host)."""
+    return min(32, os.cpu_count() or 1)
+
+
+def cpu_reference_run(cfg_name, batch, warmup, steps):
+    import torch
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
+    hp = RefHotPath(cfg_name, torch.device("cpu"))
+    img = torch.rand(batch, 3, hp.cfg["image_size"], hp.cfg["image_size"], generator=torch.Generator().manual_seed(0))
+    for _ in range(warmup):
+        hp.step(img)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        hp.step(img)
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=batch / sec, unit=UNIT, cores=threads, kind=hp.kind, host_cpus=os.cpu_count(), ms_per_step=sec * 1e3,
+                sample=f"{warmup} warm-up + {steps} timed fwd+bwd steps of {batch} images, {cfg_name} config, "
+                       f"{'reference nn.Modules (oracle/_ref)' if hp.kind == 'reference' else 'oracle port'} on torch CPU fp32, "
+                       f"{threads} threads")
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path.  /root/reference (Python, needs
-    pytorch_lightning to import as a package) cannot travel to the GPU box, so this times
-    oracle/vitvq_oracle.py, the line-by-line functional port pinned against the reference's
-    outputs (kind = "port"), with every host thread, on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU path on the box's host cores, bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = pick_cpu_threads(args.config)
-    sample_b = args.ref_batch
-    step = oracle_step(args.config, sample_b, threads)
-    for _ in range(max(1, args.warmup) if args.warmup else 0):
-        step()
-    times = [step() for _ in range(args.steps)]
-    sec = sum(times) / len(times)
-    val = sample_b / sec
+    cb = cpu_reference_run(args.config, args.ref_batch, max(1, args.warmup), max(1, args.steps))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes, synthetic 256x256, fwd+bwd, CPU sample of {sample_b} images/step",
-                   "global_batch": sample_b, "parallelism": "host threads"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-                         "sample": f"{args.steps} fwd+bwd steps of {sample_b} images, {args.config} config, torch CPU fp32, "
-                                   f"{threads} threads (fastest of a 16/32/64/all calibration)"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes, synthetic 256x256, fwd+bwd, CPU sample of {args.ref_batch} images/step",
+                   "global_batch": args.ref_batch, "parallelism": "host threads"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(cfg_name, dev, batches=(64, 48, 32, 16, 8)):
+    """the reference modules .cuda() eagerly on this B200 (cuBLAS / cuDNN / ATen): the honest 'reference on this
+    box' bar, at the largest batch that fits, with TF32 matmuls off and on"""
+    import torch
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        for B in batches:
+            hp = None
+            try:
+                hp = RefHotPath(cfg_name, dev)
+                img = torch.rand(B, 3, 256, 256, device=dev)
+                for _ in range(2):
+                    hp.step(img)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    hp.step(img)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / 3
+                out["tf32_matmul" if tf32 else "fp32_matmul"] = dict(value=B / ms * 1e3, unit=UNIT, batch=B, ms_per_step=ms,
+                                                                     peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+                break
+            except torch.OutOfMemoryError:
+                pass
+            finally:
+                del hp
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["kind"] = "reference" if reference_modules() is not None else "port"
+    out["note"] = "3 timed fwd+bwd steps after 2 warm-ups, eager PyTorch (cuBLAS/ATen), largest batch of (64,48,32,16,8) that fits"
+    return out
+
+
+def vq_block(dev, peaks):
+    """BASELINE metric part 2: the fused VQ lookup alone, M = 131072 tokens, 8192 codes, D = 32 (SURVEY.md section 8d:
+    264 B/token + 1 MiB codebook algorithmic bytes; 524288 FLOP/token/depth -- compute-bound by construction)"""
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    M, K, D = 131072, 8192, 32
+    g = torch.Generator(device="cpu").manual_seed(0)
+    E = torch.randn(K, D, generator=g).to(dev)
+    z_rand = torch.randn(M, D, generator=g).to(dev)
+    z_clu = (E[torch.randint(0, 45, (M,), generator=g).to(dev)] + 0.01 * torch.randn(M, D, generator=g).to(dev)).contiguous()
+    flush = torch.empty(160 * 2 ** 20 // 4, device=dev)           # > 126 MB L2: written between timed launches
+
+    def timed(fn, iters=5):
+        for _ in range(2):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize(dev)
+            tot += s.elapsed_time(e)
+        return tot / iters
+    res = {"tokens": M, "n_embed": K, "embed_dim": D, "l2_hygiene": "160 MB buffer written between timed launches"}
+    for name, z, depth in (("depth1", z_rand, 1), ("depth4", z_rand, 4), ("depth1_clustered", z_clu, 1)):
+        ms = timed(lambda: ops.vq_fwd(z, E, depth, 0.25))
+        bytes_alg = M * (128 + 128 + 8 * depth) + K * D * 4
+        flops = 2.0 * D * K * M * depth
+        res[name] = dict(ms=ms, gb_s=bytes_alg / ms / 1e6, gb_s_frac_of_hbm=bytes_alg / ms / 1e6 / peaks["hbm_gbs"],
+                         tflops=flops / ms / 1e9, frac_of_fp32_fma_peak=flops / ms / 1e9 / FP32_FMA_PEAK_TFLOPS)
+        _, _, idx = ops.vq_fwd(z, E, depth, 0.25)
+        g_out, g_loss = torch.randn(M, D, device=dev), torch.ones((), device=dev)
+        msb = timed(lambda: ops.vq_bwd(z, E, idx, g_out, g_loss, depth > 1, 0.25))
+        res[name]["bwd_ms"] = msb
+        res[name]["bwd_gb_s"] = (M * (392 + 8 * (depth - 1)) + K * D * 4) / msb / 1e6
+        res[name]["live_codes"] = int(idx[:, 0].unique().numel())
+    res["note"] = ("forward time includes vq_prep (codebook normalise + transpose) and the loss reduction; the lookup is FP32-FMA "
+                   "bound (1986 FLOP/B), so GB/s is a few % of HBM by construction and the kernel is graded on frac_of_fp32_fma_peak "
+                   f"(peak {FP32_FMA_PEAK_TFLOPS:.1f} TFLOP/s = 148 SM x 128 lanes x 2 x 1.965 GHz)")
+    return res
 
 
 def main():
@@ -149,9 +270,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="base", choices=["tiny", "small", "base", "base_rq4", "large"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--precision", default=None, choices=["fp16", "tf32", "parity"], help="data path (default: fp16)")
     ap.add_argument("--cta-group", type=int, default=int(os.environ.get("B200VQ_CTA_GROUP", "2")))
     ap.add_argument("--ref-batch", type=int, default=4, help="images per CPU step for --impl reference / cpu_baseline")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", action="store_true", help="torch DistributedDataParallel (overlapped buckets) instead of one flat all-reduce")
+    ap.add_argument("--extras", default="vq,secondary,eager,cpu",
+                    help="comma list of the 1-GPU extra blocks to measure after the timed regions: vq, secondary, eager, cpu ('' = none)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -161,7 +285,7 @@ def main():
     import torch.nn as nn
 
     import enhancing_transformers_b200 as etb
-    from oracle import vitvq_oracle as O   # FLOP model + config table + cpu_baseline leg only
+    from enhancing_transformers_b200.configs import CONFIGS, flops_per_image, gemm_flops_per_image
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,51 +297,73 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     etb.functional.GEMM_CTA_GROUP = args.cta_group
-
-    cfg = O.CONFIGS[args.config]
-    e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
+    if args.precision:
+        etb.set_precision(args.precision)
+    precision = etb.get_precision()
 
     class HotPath(nn.Module):
         """the five modules of ViTVQ.forward (vitvqgan.py:35-39,44-72) + the bench loss"""
 
-        def __init__(self):
+        def __init__(self, cfg):
             super().__init__()
+            e, d, q = cfg["encoder"], cfg["decoder"], cfg["quantizer"]
             self.encoder = etb.ViTEncoder(cfg["image_size"], cfg["patch_size"], **e)
             self.decoder = etb.ViTDecoder(cfg["image_size"], cfg["patch_size"], **d)
             self.quantizer = etb.VectorQuantizer(**q)
-            self.pre_quant = nn.Linear(e["dim"], q["embed_dim"])
-            self.post_quant = nn.Linear(q["embed_dim"], d["dim"])
+            self.pre_quant = etb.QuantLinear(e["dim"], q["embed_dim"])
+            self.post_quant = etb.QuantLinear(q["embed_dim"], d["dim"])
 
         def forward(self, x):
             quant, qloss, _ = self.quantizer(self.pre_quant(self.encoder(x)))
             rec = self.decoder(self.post_quant(quant))
             return ((rec - x) ** 2).mean() + qloss
 
-    torch.manual_seed(0)
-    model = HotPath().to(dev)
-    net = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
-    B = args.batch
-    gen = torch.Generator().manual_seed(1234 + rank)
-    host_imgs = torch.rand(B, 3, cfg["image_size"], cfg["image_size"], generator=gen).pin_memory()
-    dev_imgs = host_imgs.to(dev, non_blocking=True)
-    torch.cuda.synchronize()
-
-    def step(x):
-        for p in model.parameters():
-            p.grad = None
-        loss = net(x)
-        loss.backward()
-        return loss
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def make_step(model, net, comm_events=None):
+        params = list(model.parameters())
+
+        def step(x, second_forward=False):
+            for p in params:
+                p.grad = None
+            if second_forward:                 # the reference training_step runs forward twice per batch (vitvqgan.py:101-127)
+                with torch.no_grad():
+                    net(x)
+            loss = net(x)
+            loss.backward()
+            if world > 1 and not args.ddp:
+                if comm_events is not None:
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    etb.allreduce_gradients(params)
+                    e.record()
+                    comm_events.append((s, e))
+                else:
+                    etb.allreduce_gradients(params)
+            return loss
+        return step
+
+    cfg = CONFIGS[args.config]
+    torch.manual_seed(0)
+    model = HotPath(cfg).to(dev)
+    net = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if (world > 1 and args.ddp) else model
+    B = args.batch
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_imgs = [torch.rand(B, 3, cfg["image_size"], cfg["image_size"], generator=gen).pin_memory() for _ in range(2)]
+    dev_imgs = host_imgs[0].to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    comm_events = []
+    step = make_step(model, net, comm_events)
+
     # ---- warm-up -----------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(dev_imgs)
     barrier()
+    comm_events.clear()
 
     # ---- device-resident timed region (value) + per-GEMM events (roofline) -------------------
     gemm_events = []
@@ -228,14 +374,14 @@ def main():
         s.record()
         out = orig_gemm(a, b, M, N, K, **kw)
         t.record()
-        gemm_events.append((s, t, 2.0 * M * N * K * kw.get("splits", 1)))
+        passes = 3 if kw.get("a_lo") is not None else 1
+        gemm_events.append((s, t, 2.0 * M * N * K * kw.get("splits", 1), a.dtype == torch.float16, passes))
         return out
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     etb.ops.gemm = timed_gemm
-    etb.functional.ops.gemm = timed_gemm
     launches0 = etb.ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -246,68 +392,127 @@ def main():
     barrier()
     launches = etb.ops.launch_count() - launches0
     etb.ops.gemm = orig_gemm
-    etb.functional.ops.gemm = orig_gemm
     ms_total = ev0.elapsed_time(ev1)
-    gemm_ms = sum(s.elapsed_time(t) for s, t, _ in gemm_events)
-    gemm_flops = sum(f for _, _, f in gemm_events)
+    gemm_ms = sum(s.elapsed_time(t) for s, t, *_ in gemm_events)
+    gemm_flops = sum(f for _, _, f, *_ in gemm_events)
+    f16_ms = sum(s.elapsed_time(t) for s, t, _, h, _ in gemm_events if h)
+    f16_flops = sum(f for _, _, f, h, _ in gemm_events if h)
     n_gemm = len(gemm_events)
+    comm_ms = sum(s.elapsed_time(e) for s, e in comm_events) / max(1, args.steps)
+    comm_events.clear()
 
-    # ---- end-to-end timed region: pinned host images in, loss out, every step ------------------
+    # ---- end-to-end timed region: pinned host images in (prefetched on a copy stream), loss out, every step ----
+    copy_stream = torch.cuda.Stream(device=dev)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     last = 0.0
-    for _ in range(args.steps):
-        x = host_imgs.to(dev, non_blocking=True)
-        last = float(step(x).item())      # device -> host read of the step's result
+    with torch.cuda.stream(copy_stream):
+        nxt = host_imgs[0].to(dev, non_blocking=True)
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        x = nxt
+        x.record_stream(torch.cuda.current_stream())
+        if i + 1 < args.steps:
+            with torch.cuda.stream(copy_stream):       # step i+1's images travel while step i computes
+                nxt = host_imgs[(i + 1) % 2].to(dev, non_blocking=True)
+        last = float(step(x).item())                   # device -> host read of the step's result
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, ms_e2e, comm_ms], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [float(g[0]) / args.steps for g in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, comm_ms = float(t[0]), float(t[1]), float(t[2])
 
+    line = None
     if rank == 0:
         peaks = load_peaks()
         imgs = world * B * args.steps
         value = imgs / (ms_total / 1e3)
         e2e = imgs / (ms_e2e / 1e3)
-        flops_step = 3.0 * O.flops_per_image(cfg) * B
+        flops_step = 3.0 * flops_per_image(cfg) * B
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
+        kern = {"fp16": "gemm_tc_kernel<KIND=f16> (tcgen05 kind::f16, fp32 accumulate)", "tf32": "gemm_tc_kernel<KIND=tf32> (tcgen05 kind::tf32)",
+                "parity": "gemm_tc_kernel<KIND=tf32>, 3 passes (3xTF32)"}[precision]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
+            "dtype": {"fp16": "fp16 operands / fp32 accumulate (block GEMMs), tf32 (attention core), fp32 (everything else)",
+                      "tf32": "tf32", "parity": "3xtf32 (fp32-grade)"}[precision], "data": "synthetic",
             "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes (ViT-VQGAN-{args.config}), synthetic 256x256x3, "
                                    f"fwd+bwd, batch {B}/GPU", "global_batch": world * B, "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "l2_hygiene": "inputs_exceed_l2 (activations >> 126 MB per step)",
-                       "gemm_cta_group": args.cta_group, "precision": "tf32 tensor-core GEMM/attention (rn-rounded operands, fp32 accumulate); fp32 VQ/LayerNorm"},
+                       "gemm_cta_group": args.cta_group, "precision": precision,
+                       "grad_reduce": ("torch DDP buckets (overlapped)" if args.ddp else "one flat NCCL all-reduce after backward") if world > 1 else "none"},
             "model_tflops_per_gpu": flops_step / (ms_total / args.steps / 1e3) / 1e12,
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_imgs[0].numel() * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "last_loss": last,
+                    "note": "images prefetched from pinned host memory on a copy stream (step i+1 travels while step i computes); loss.item() every step"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 1.562e9 if args.config == "base" and B == 128 else None,
-                         "traffic_note": "dram read+write bytes of one to_qkv launch (M=131072 N=2304 K=768) from profiles/ ncu --set full; "
-                                         "algorithmic bytes of that launch: 1.618e9",
-                         "peak_source": peaks["source"] + ": cuBLAS bf16 sustained; tf32 issues at half the bf16 rate, so frac <= ~0.5 by construction",
-                         "frac_of_half_rate_peak": achieved / (peak / 2), "launches_timed": n_gemm,
-                         "share_of_step": gemm_ms / ms_total, "hbm_peak_gbs": peaks["hbm_gbs"]},
+                         "traffic": None,
+                         "traffic_note": "see profiles/r02_ncu_gemm_f16.txt (ncu --set full dram bytes of one to_qkv launch vs its algorithmic bytes)",
+                         "peak_source": peaks["source"] + ": cuBLAS bf16 sustained (kind::f16 issues at the bf16 rate; kind::tf32 at half of it)",
+                         "launches_timed": n_gemm, "share_of_step": gemm_ms / ms_total,
+                         "algorithmic_gemm_tflop_per_step": 3.0 * gemm_flops_per_image(cfg) * B / 1e12,
+                         "f16_gemms": {"achieved": f16_flops / (f16_ms / 1e3) / 1e12 if f16_ms > 0 else None,
+                                       "frac": f16_flops / (f16_ms / 1e3) / 1e12 / peak if f16_ms > 0 else None,
+                                       "share_of_step": f16_ms / ms_total},
+                         "hbm_peak_gbs": peaks["hbm_gbs"]},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = pick_cpu_threads(args.config)
-            cstep = oracle_step(args.config, args.ref_batch, threads)
-            sec = cstep()
-            line["cpu_baseline"] = {"value": args.ref_batch / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "host_cpus": os.cpu_count(),
-                                    "sample": f"1 fwd+bwd step of {args.ref_batch} images, {args.config} config, oracle port on "
-                                              f"torch CPU fp32, {threads} threads (fastest of a 16/32/64/all calibration)"}
+        if world > 1:
+            line["comm"] = {"allreduce_ms": comm_ms if not args.ddp else None, "exposed_ms": comm_ms if not args.ddp else None,
+                            "per_rank_ms_per_step": per_rank,
+                            "note": "flat all-reduce issued after backward on the compute stream: all of it is exposed; "
+                                    "per_rank separates the slowest-GPU effect from communication" if not args.ddp else
+                                    "DDP: bucketed all-reduce overlapped with backward on NCCL's stream"}
+    del model, net, step
+    torch.cuda.empty_cache()
+
+    # ---- extras (rank 0, one GPU): VQ block, secondary configs, eager-GPU reference, CPU reference --------------
+    extras = set(x for x in args.extras.split(",") if x) if (rank == 0 and world == 1) else set()
+    if "vq" in extras:
+        line["vq"] = vq_block(dev, peaks)
+    if "secondary" in extras:
+        sec = {}
+        for name, cname, b, second in (("base_rq4_B128", "base_rq4", 128, False), ("large_B32", "large", 32, False),
+                                       ("base_B128_2fwd_1bwd", "base", 128, True)):
+            torch.manual_seed(0)
+            m2 = HotPath(CONFIGS[cname]).to(dev)
+            st = make_step(m2, m2)
+            x = torch.rand(b, 3, 256, 256, device=dev)
+            for _ in range(3):
+                st(x, second)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                st(x, second)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 3
+            sec[name] = dict(value=b / ms * 1e3, unit=UNIT, ms_per_step=ms, batch=b,
+                             model_tflops=(4.0 if second else 3.0) * flops_per_image(CONFIGS[cname]) * b / ms / 1e9)
+            del m2, st, x
+            torch.cuda.empty_cache()
+        sec["note"] = ("3 timed steps after 3 warm-ups each; base_rq4 = BASELINE config 3 (use_residual, num_quantizers=4); large_B32 = the per-GPU "
+                       "share of BASELINE config 4 (batch 256 over 8 GPUs); 2fwd_1bwd = the reference training_step shape (vitvqgan.py:101-127)")
+        line["secondary"] = sec
+    if "eager" in extras:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(args.config, dev)
+    if "cpu" in extras:
+        line["cpu_baseline"] = cpu_reference_run(args.config, args.ref_batch, 1, 3)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -69,7 +69,7 @@ _SHADOW_ATTR = "_b200vq_shadows"
 _SHADOW_MAKERS = {"tf32": ops.round_tf32, "f16": ops.to_half, "lo": ops.split_tf32_lo}
 
 
-def weight_shadow(w: Tensor, kind: str) -> Tensor:
+def weight_shadow(w: Tensor, kind: str, in_backward: bool = False) -> Tensor:
     """Tensor-core copy of a parameter.  The copies hang off the parameter object itself (so they live
     and die with it -- a global cache keyed by address would hand a new parameter allocated at a recycled
     address the previous owner's values).
@@ -80,10 +80,12 @@ def weight_shadow(w: Tensor, kind: str) -> Tensor:
     those swaps happen and no optimizer runs -- the shadow is simply recomputed on every call (0.1 ms for
     the whole base model), and `invalidate_shadows()` exists for the remaining case (a ``.data`` write
     between two grad-enabled forwards).  A refresh always writes a *new* buffer: the old one may be held
-    by ``ctx.save_for_backward`` of a graph that has not run backward yet."""
+    by ``ctx.save_for_backward`` of a graph that has not run backward yet.  Backward nodes (`in_backward`) save
+    the parameter itself, so autograd has already verified its version when they ask: the cached copy is valid
+    there although gradient recording is off."""
     cache = getattr(w, _SHADOW_ATTR, None)
     key = (w._version, w.data_ptr())
-    if cache is not None and torch.is_grad_enabled():
+    if cache is not None and (in_backward or torch.is_grad_enabled()):
         ent = cache.get(kind)
         if ent is not None and ent[0] == key and ent[1].device == w.device:
             return ent[1]
@@ -117,13 +119,13 @@ class _W:
     """operand view of one weight for the current precision: `.a` (+ `.lo` in parity mode)"""
     __slots__ = ("a", "lo")
 
-    def __init__(self, w: Tensor, mode: str):
+    def __init__(self, w: Tensor, mode: str, in_backward: bool = False):
         if mode == "parity":
             src = w.detach()
             self.a = src if src.is_contiguous() else src.contiguous()
-            self.lo = weight_shadow(w, "lo")
+            self.lo = weight_shadow(w, "lo", in_backward)
         else:
-            self.a = weight_shadow(w, "f16" if mode == "fp16" else "tf32")
+            self.a = weight_shadow(w, "f16" if mode == "fp16" else "tf32", in_backward)
             self.lo = None
 
 
@@ -211,7 +213,7 @@ def _block_bwd_fp32(saved, prm, dims, mode, g, g_colsum, need_w):
     M, D = x.shape
     inner, mlp, scale = heads * dh, w1.shape[0], dh ** -0.5
     rnd = mode == "tf32"
-    wq, wo, w1s, w2s = (_W(w, mode) for w in (w_qkv, w_out, w1, w2))
+    wq, wo, w1s, w2s = (_W(w, mode, True) for w in (w_qkv, w_out, w1, w2))
     # ---- feed-forward branch
     db2 = (g_colsum if g_colsum is not None else ops.colsum(g)) if need_w else None
     dw2 = _wgrad(g, t, D, mlp, mode) if need_w else None
@@ -270,7 +272,7 @@ def _block_bwd_f16(saved, prm, dims, g, g_colsum, gh, sc, need_w):
     inner, mlp, scale = heads * dh, w1.shape[0], dh ** -0.5
     cg = GEMM_CTA_GROUP
     S, inv = sc[0:1], sc[1:2]
-    wq, wo, w1h, w2h = (weight_shadow(w, "f16") for w in (w_qkv, w_out, w1, w2))
+    wq, wo, w1h, w2h = (weight_shadow(w, "f16", True) for w in (w_qkv, w_out, w1, w2))
     # ---- feed-forward branch
     db2 = (g_colsum if g_colsum is not None else ops.colsum(g)) if need_w else None
     dw2 = _wgrad(gh, t, D, mlp, inv_scale=inv) if need_w else None
@@ -411,7 +413,7 @@ class LinearFn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
         db = ops.colsum(gr) if (has_bias and need_b) else None
         dw = _wgrad(gr, xr, N, K, mode) if need_w else None
-        dx = _mm(gr, _W(w, mode), M, K, N, mode, b_major=1) if need_x else None
+        dx = _mm(gr, _W(w, mode, True), M, K, N, mode, b_major=1) if need_x else None
         return dx, dw, db, None, None
 
 
@@ -479,7 +481,7 @@ class PatchEmbedFn(torch.autograd.Function):
         dw = _wgrad(g, patches, D, pd, mode).view_as(w) if ctx.needs_input_grad[1] else None
         dimg = None
         if ctx.needs_input_grad[0]:
-            ws = _W(w, mode)
+            ws = _W(w, mode, True)
             ws.a = ws.a.view(D, pd)
             if ws.lo is not None:
                 ws.lo = ws.lo.view(D, pd)
@@ -524,7 +526,7 @@ class ToPixelFn(torch.autograd.Function):
         dw = _wgrad(x, dy, D, pd, mode).view_as(w) if need_w else None
         dx = None
         if need_x:
-            ws = _W(w, mode)
+            ws = _W(w, mode, True)
             ws.a = ws.a.view(D, pd)
             if ws.lo is not None:
                 ws.lo = ws.lo.view(D, pd)

@@ -32,17 +32,25 @@ class OracleNet(torch.nn.Module):
         return O.vitvq_loss(sd, img, CFG)[0]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, flat):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import vitvq_oracle as O
     torch.set_num_threads(1)
     sd = O.init_vitvq_sd(CFG, seed=0)
     imgs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1))
-    net = torch.nn.parallel.DistributedDataParallel(OracleNet(sd))
     shard = imgs[rank * 2:(rank + 1) * 2]                       # even split, as main.py's DDP does
-    net(shard).backward()
-    grads = {n: p.grad.clone() for n, p in zip(net.module.names, net.module.params) if p.grad is not None}
+    if flat:      # the package's own reduction (what bench.py uses on the GPUs): one flat all-reduce after backward
+        from enhancing_transformers_b200.parallel import allreduce_gradients
+        local = OracleNet(sd)
+        local(shard).backward()
+        allreduce_gradients(local.parameters())
+        names, params = local.names, local.params
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(OracleNet(sd))
+        net(shard).backward()
+        names, params = net.module.names, net.module.params
+    grads = {n: p.grad.clone() for n, p in zip(names, params) if p.grad is not None}
     if rank == 0:
         single = OracleNet(sd)
         single(imgs).backward()
@@ -57,14 +65,18 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_ddp_gradients_equal_single_process():
+import pytest
+
+
+@pytest.mark.parametrize("flat", [False, True], ids=["torch_ddp", "flat_allreduce"])
+def test_sharded_ddp_gradients_equal_single_process(flat):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, flat)) for r in range(2)]
     for p in procs:
         p.start()
     worst = q.get(timeout=180)

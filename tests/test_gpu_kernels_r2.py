@@ -104,8 +104,8 @@ def test_gemm_3xtf32_is_fp32_grade(cg, M, N, K):
     c3 = ops.gemm(a, b, M, N, K, a_lo=ops.split_tf32_lo(a), b_lo=ops.split_tf32_lo(b), cta_group=cg)
     c1 = ops.gemm(a, b, M, N, K, cta_group=cg)
     e3, e1 = relerr(c3, ref), relerr(c1, ref)
-    assert e3 < 3e-6, e3                 # fp32 sgemm-level
-    assert e1 > 20 * e3                  # and far better than the single truncating pass
+    assert e3 < 2e-6 * max(1.0, (K / 256) ** 0.5), e3      # fp32 sgemm-level (grows like sqrt(K): fp32 accumulation)
+    assert e1 > 20 * e3                                      # and far better than the single truncating pass
 
 
 def test_gemm_3xtf32_dgrad_and_wgrad_forms():
@@ -138,7 +138,7 @@ def test_attention_exact_fwd_bwd(B, N, heads, dh):
     q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
     s = (q @ k.transpose(-1, -2)) * scale
     oref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, inner)
-    assert relerr(o, oref.detach()) < 5e-6
+    assert relerr(o, oref.detach()) < 3e-5                   # exp2f (2 ulp) on scores up to ~|15|: fp32-grade, not tf32-grade (1e-4)
     assert relerr(lse, torch.logsumexp(s, -1).reshape(-1).detach()) < 2e-6
     do = torch.randn(B * N, inner, device="cuda")
     oref.backward(do.double())
