@@ -31,6 +31,8 @@ _SIGNATURES = {
     "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
     "b200vq_attention_fwd": (c_i, [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "b200vq_attention_bwd": (c_i, [c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
+    "b200vq_attention_f16_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
+    "b200vq_attention_f16_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "b200vq_attention_exact_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "b200vq_attention_exact_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),
     "b200vq_vq_workspace_bytes": (c_sz, [c_i, c_i, c_i]),

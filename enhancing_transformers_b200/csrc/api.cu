@@ -71,6 +71,8 @@ int layernorm_backward(const float*, const float*, const float*, const float*, c
 int attention_forward(const float*, void*, int, float*, int, int, int, int, float, int, cudaStream_t);
 int attention_backward(const float*, const void*, int, const float*, const float*, void*, int, const float*, float*, int, int,
                        int, int, float, int, cudaStream_t);
+int attention_f16_forward(const void*, void*, float*, int, int, int, int, float, cudaStream_t);
+int attention_f16_backward(const void*, const void*, const float*, const void*, void*, float*, int, int, int, int, float, cudaStream_t);
 int attention_exact_forward(const float*, float*, float*, int, int, int, int, float, cudaStream_t);
 int attention_exact_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float,
                              cudaStream_t);
@@ -149,6 +151,13 @@ int b200vq_attention_bwd(const float* qkv, const void* out, int out_half, const 
                          int round_out, void* stream) {
   return attention_backward(qkv, out, out_half, lse, dout, dqkv, dqkv_half, dqkv_scale, delta, B, N, heads, dh, scale,
                             round_out, S(stream));
+}
+int b200vq_attention_f16_fwd(const void* qkv16, void* out16, float* lse, int B, int N, int heads, int dh, float scale, void* stream) {
+  return attention_f16_forward(qkv16, out16, lse, B, N, heads, dh, scale, S(stream));
+}
+int b200vq_attention_f16_bwd(const void* qkv16, const void* out16, const float* lse, const void* dout16, void* dqkv16, float* delta,
+                             int B, int N, int heads, int dh, float scale, void* stream) {
+  return attention_f16_backward(qkv16, out16, lse, dout16, dqkv16, delta, B, N, heads, dh, scale, S(stream));
 }
 int b200vq_attention_exact_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
                                void* stream) {

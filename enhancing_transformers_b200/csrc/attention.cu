@@ -16,24 +16,25 @@ int attention_backward_tc(const float*, const float*, const float*, const float*
 // delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d].  HBM-bound: one float4 of O and dO per thread, dh/4 adjacent
 // lanes per (row, head) reduced with shuffles, so a warp streams 512 contiguous bytes of each tensor.
 // O is fp32, or fp16 (OHALF) when the forward stored it for an fp16 to_out GEMM.
-template <int LANES, int OHALF>   // lanes per (row, head) = dh / 4: 16 (dh 64) or 8 (dh 32)
+template <int LANES, int OHALF, int DHALF>   // lanes per (row, head) = dh / 4: 16 (dh 64) or 8 (dh 32)
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const void* __restrict__ o, const float* __restrict__ dout, float* __restrict__ delta, long long groups,
+attn_delta_kernel(const void* __restrict__ o, const void* __restrict__ dout, float* __restrict__ delta, long long groups,
                   int N, int heads) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long total = groups * LANES;          // one thread per float4
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ((total + 31) / 32) * 32; i += stride) {
     float s = 0.f;
     if (i < total) {
-      float4 a;
-      if constexpr (OHALF) {
-        const uint2 h = reinterpret_cast<const uint2*>(o)[i];
-        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-        a = make_float4(lo.x, lo.y, hi.x, hi.y);
-      } else {
-        a = reinterpret_cast<const float4*>(o)[i];
-      }
-      const float4 b = reinterpret_cast<const float4*>(dout)[i];
+      auto load4 = [i](const void* ptr, bool half) {
+        if (half) {
+          const uint2 h = reinterpret_cast<const uint2*>(ptr)[i];
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+          return make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        return reinterpret_cast<const float4*>(ptr)[i];
+      };
+      const float4 a = load4(o, OHALF != 0);
+      const float4 b = load4(dout, DHALF != 0);
       s = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
     }
 #pragma unroll
@@ -55,7 +56,7 @@ int attention_forward(const float* qkv, void* out, int out_half, float* lse, int
   return attention_forward_tc(qkv, out, out_half, lse, B, N, heads, dh, scale, round_out, stream);
 }
 
-int attention_delta(const void* out, int out_half, const float* dout, float* delta, int B, int N, int heads, int dh,
+int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
                     cudaStream_t stream) {
   const long long groups = (long long)B * N * heads;
   const long long threads = groups * (dh / 4);
@@ -63,13 +64,19 @@ int attention_delta(const void* out, int out_half, const float* dout, float* del
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   const unsigned g = (unsigned)blocks;
+#define B200_DELTA(L, OH, DHF) attn_delta_kernel<L, OH, DHF><<<g, 256, 0, stream>>>(out, dout, delta, groups, N, heads)
   if (dh == 64) {
-    if (out_half) attn_delta_kernel<16, 1><<<g, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
-    else          attn_delta_kernel<16, 0><<<g, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
+    if (out_half && dout_half) B200_DELTA(16, 1, 1);
+    else if (out_half)         B200_DELTA(16, 1, 0);
+    else if (dout_half)        B200_DELTA(16, 0, 1);
+    else                       B200_DELTA(16, 0, 0);
   } else {
-    if (out_half) attn_delta_kernel<8, 1><<<g, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
-    else          attn_delta_kernel<8, 0><<<g, 256, 0, stream>>>(out, dout, delta, groups, N, heads);
+    if (out_half && dout_half) B200_DELTA(8, 1, 1);
+    else if (out_half)         B200_DELTA(8, 1, 0);
+    else if (dout_half)        B200_DELTA(8, 0, 1);
+    else                       B200_DELTA(8, 0, 0);
   }
+#undef B200_DELTA
   B200_LAUNCH_OK("attn_delta_kernel");
   return 0;
 }
@@ -79,7 +86,7 @@ int attention_backward(const float* qkv, const void* out, int out_half, const fl
                        int round_out, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
-  int rc = attention_delta(out, out_half, dout, delta, B, N, heads, dh, stream);
+  int rc = attention_delta(out, out_half, dout, 0, delta, B, N, heads, dh, stream);
   if (rc) return rc;
   return attention_backward_tc(qkv, dout, lse, delta, dqkv, dqkv_half, dqkv_scale, B, N, heads, dh, scale, round_out, stream);
 }

@@ -405,7 +405,8 @@ static int exact_bwd_launch(const float* qkv, const float* dout, const float* ls
 }
 
 // delta = rowsum(dO * O) through the shared helper of attention.cu
-int attention_delta(const void* out, int out_half, const float* dout, float* delta, int B, int N, int heads, int dh, cudaStream_t stream);
+int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
+                    cudaStream_t stream);
 
 int attention_exact_forward(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
                             cudaStream_t stream) {
@@ -421,7 +422,7 @@ int attention_exact_backward(const float* qkv, const float* out, const float* ls
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
-  int rc = attention_delta(out, 0, dout, delta, B, N, heads, dh, stream);
+  int rc = attention_delta(out, 0, dout, 0, delta, B, N, heads, dh, stream);
   if (rc) return rc;
   if (dh == 64) return exact_bwd_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, stream);
   return exact_bwd_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, stream);

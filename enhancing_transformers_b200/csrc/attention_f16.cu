@@ -1,0 +1,828 @@
+// fp16-operand flash-attention forward and backward on tcgen05 / TMEM (reference layers.py:124-130), dim_head = 64.
+//
+// The same warp-specialised structure as attention_tc.cu (TMA producer, two MMA-issuing warps, eight softmax
+// warps with a query row shared by two threads) with every tensor-core operand in fp16 (kind::f16, fp32
+// accumulation in TMEM): q/k/v arrive as the fp16 output of the to_qkv GEMM, dO as the fp16 (gradient-scaled) output of
+// the to_out dgrad GEMM, and P / dS are written back to TMEM as packed fp16 pairs.  fp16 carries the same 11-bit
+// significand as the tf32 operands of attention_tc.cu, so the numerics are unchanged; what changes is
+//   * every MMA does twice the work per issue slot (UMMA_K = 16) -- the backward kernels sat on their MMA-issue floor;
+//   * a 64-wide head row is exactly one 128-byte swizzle row, so ONE shared-memory image of a tile serves both as a
+//     K-major operand (rows = M/N index) and as an MN-major operand (rows = contraction index): the second TMA fetch of
+//     Q / dO / K with a different swizzle that the tf32 kernels need disappears, and tiles are half the bytes;
+//   * P / dS take half the TMEM columns and half the tcgen05.st traffic.
+// Gradients: dO carries the power-of-two gradient scale S of the backward segment (functional.py), and so do delta,
+// dS and the dq / dk / dv this kernel stores (fp16): everything is linear in dO, nothing is rescaled here.
+#include "common.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kThreads = 352;      // warp 0 TMA, warp 1 MMA issuer A, warps 2..9 softmax (two per TMEM lane quarter), warp 10 MMA issuer B
+constexpr int kIssuerB = 10;
+constexpr int DH = 64;             // head dim: one 128-byte row of fp16
+constexpr int kTile128 = 128 * 128;   // bytes of a 128-row tile
+constexpr int kTile64 = 64 * 128;     // bytes of a 64-row tile
+constexpr float kLog2eF = 1.4426950408889634f;
+constexpr int kBoxBytes = 8 * 4096;   // one store box per softmax warp
+
+__device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem], fp16 inputs: A holds M = 128 rows (lanes) x K = 16 as 8 columns of packed pairs
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {      // values known to be in fp16 range
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 32 rows x 32 values -> fp16 (x mul, saturating) -> 32-row x 64-byte un-swizzled box -> one TMA store
+__device__ __forceinline__ void store_box_h(uint8_t* box, const CUtensorMap* tm, const float (&r)[32], float mul, int c0, int c1, int c2,
+                                            int lane) {
+  if (lane == 0) bulk_wait_group_read<0>();
+  __syncwarp();
+  uint8_t* rowp = box + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    pk.x = pack_half2_sat(r[8 * j] * mul, r[8 * j + 1] * mul);
+    pk.y = pack_half2_sat(r[8 * j + 2] * mul, r[8 * j + 3] * mul);
+    pk.z = pack_half2_sat(r[8 * j + 4] * mul, r[8 * j + 5] * mul);
+    pk.w = pack_half2_sat(r[8 * j + 6] * mul, r[8 * j + 7] * mul);
+    *reinterpret_cast<uint4*>(rowp + j * 16) = pk;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, box, c0, c1, c2);
+    bulk_commit_group();
+  }
+}
+
+// K-major operand descriptor of a tile whose rows are 128 bytes (64 fp16): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t kmajor_desc(const void* tile) { return make_smem_desc(smem_u32(tile), 16, 1024, kLayoutSw128); }
+// the same image read as an MN-major B operand (rows = contraction index, 64 columns = N): one 64-wide atom
+__device__ __forceinline__ uint64_t mnmajor_desc(const void* tile) { return make_smem_desc(smem_u32(tile), 8192, 1024, kLayoutSw128); }
+constexpr uint32_t kKStepK = 32;        // K-major: 16 fp16 along the row
+constexpr uint32_t kKStepMN = 2048;     // MN-major: 16 rows of 128 bytes
+
+struct FwdParams {
+  float* lse;        // [B*heads*N]
+  int N, heads, q_tiles, kv_tiles, total_items;
+  float scale;
+};
+
+// =============================================================================================
+// forward: work item = (batch, head, 128-query tile)
+// TMEM columns: S buffers [0,128) [128,256) (P packed over the first 64 columns of its S), PV [256,320) [320,384)
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + kTile128;            // [2]
+  uint8_t* Vs = smem + 3 * kTile128;        // [2]
+  uint8_t* obox = smem + 5 * kTile128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2]
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* o_full = bars + 14;   // [2]
+  uint64_t* o_empty = bars + 16;  // [2]
+  uint64_t* sfree = bars + 18;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
+      mbar_init(&sfree[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int T = p.kv_tiles;
+
+  if (warp == 0) {
+    uint32_t kv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, kTile128);
+        tma_load_3d(Qs, &tmQKV, q_full, h * DH, qt * 128, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int s = kv_it & 1;
+        const uint32_t ph = (kv_it >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[s], kTile128);
+          tma_load_3d(Ks + s * kTile128, &tmQKV, &k_full[s], inner + h * DH, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[s], kTile128);
+          tma_load_3d(Vs + s * kTile128, &tmQKV, &v_full[s], 2 * inner + h * DH, j * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- issuer A: S_j = Q K_j^T
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+    const uint64_t qd = kmajor_desc(Qs);
+    const uint64_t kd0 = kmajor_desc(Ks);
+    uint32_t s_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      for (int j = 0; j < T; ++j, ++s_it) {
+        const int s = s_it & 1;
+        const uint32_t ph = (s_it >> 1) & 1;
+        mbar_wait(&k_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = desc_advance(kd0, s * kTile128);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + s * 128, desc_advance(qd, k * kKStepK), desc_advance(kd, k * kKStepK), idesc_s, k != 0);
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&k_empty[s]);
+          if (j == T - 1) umma_commit<1>(q_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: O_j = P_j V_j (A = packed fp16 P from TMEM, B = V read MN-major)
+    constexpr uint32_t idesc_o = make_idesc_f16(128, DH, 0, 1);
+    const uint64_t vd0 = mnmajor_desc(Vs);
+    uint32_t pv_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      for (int j = 0; j < T; ++j, ++pv_it) {
+        const int s = pv_it & 1;
+        const uint32_t ph = (pv_it >> 1) & 1;
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&o_empty[s], ph ^ 1);
+        mbar_wait(&p_full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = desc_advance(vd0, s * kTile128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // 128 keys = 8 x UMMA_K
+            umma_f16_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * kKStepMN), idesc_o, k != 0);
+          umma_commit<1>(&o_full[s]);
+          umma_commit<1>(&v_empty[s]);
+          umma_commit<1>(&sfree[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- softmax / output warps (see attention_tc.cu for the commentary; identical structure)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const int qt = w % p.q_tiles;
+      const int bh = w / p.q_tiles;
+      const int h = bh % p.heads, b = bh / p.heads;
+      float o[OC];
+#pragma unroll
+      for (int i = 0; i < OC; ++i) o[i] = 0.f;
+      float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+      auto fold_pv = [&](uint32_t it, float alpha) {
+        const int sp = it & 1;
+        uint32_t v[OC];
+        tmem_ld_32x32(tmem_base + lane_off + 256 + sp * 64 + half * OC, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[sp]);
+      };
+      uint32_t v0[32], v1[32];
+      mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
+      tcgen05_fence_after();
+      {
+        const uint32_t s0 = tmem_base + lane_off + (t_it & 1) * 128 + half * 64;
+        tmem_ld_32x32(s0, v0);
+        tmem_ld_32x32(s0 + 32, v1);
+      }
+      tmem_ld_wait();
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        const int kv_left = p.N - j * 128 - half * 64;
+        if (kv_left < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_left) v0[i] = 0xff800000u;
+            if (32 + i >= kv_left) v1[i] = 0xff800000u;
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        float* xs = xch + (t_it & 1) * 256;
+        xs[half * 128 + row_in_tile] = mx;
+        pair_bar(q);        // also orders the partner's S loads before this thread's packed P stores (they overlap its columns)
+        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx((m - m_new) * c);
+        const float mc = m_new * c;
+        float sum = 0.f, sum1 = 0.f;
+        uint32_t pk[32];       // this thread's 64 probabilities as 32 packed fp16 pairs (keys half*64 + 2i, +1)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = ex2_approx(fmaf(__uint_as_float(v0[2 * i]), c, -mc));
+          const float a1 = ex2_approx(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc));
+          const float b0 = ex2_approx(fmaf(__uint_as_float(v1[2 * i]), c, -mc));
+          const float b1 = ex2_approx(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc));
+          sum += a0 + a1; sum1 += b0 + b1;
+          pk[i] = pack_h2(a0, a1);
+          pk[16 + i] = pack_h2(b0, b1);
+        }
+        sum += sum1;
+        tmem_st_32x32(tmem_base + lane_off + s * 128 + half * 32, pk);     // P columns [0,64) of the S buffer
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+        l = fmaf(l, alpha, sum);
+        const bool more = j + 1 < T;
+        const uint32_t ph_s = ((t_it + 1) >> 1) & 1, ph_o = ((t_it - 1) >> 1) & 1;
+        if (more && j >= 1) mbar_wait2(&s_full[s ^ 1], ph_s, &o_full[s ^ 1], ph_o);
+        else if (more)      mbar_wait(&s_full[s ^ 1], ph_s);
+        else if (j >= 1)    mbar_wait(&o_full[s ^ 1], ph_o);
+        tcgen05_fence_after();
+        if (more) {
+          const uint32_t sn = tmem_base + lane_off + (s ^ 1) * 128 + half * 64;
+          tmem_ld_32x32(sn, v0);
+          tmem_ld_32x32(sn + 32, v1);
+        }
+        if (j >= 1) fold_pv(t_it - 1, alpha_prev);
+        else        tmem_ld_wait();
+        alpha_prev = alpha;
+        m = m_new;
+      }
+      mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
+      tcgen05_fence_after();
+      fold_pv(t_it - 1, alpha_prev);
+      float* ls = xch + 512;
+      ls[half * 128 + row_in_tile] = l;
+      pair_bar(q);
+      l += ls[(half ^ 1) * 128 + row_in_tile];
+      const int row = qt * 128 + row_in_tile;
+      store_box_h(obox + (warp - 2) * 4096, &tmO, o, 1.f / l, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+      if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
+      pair_bar(q);
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
+// backward (two kernels, no atomics; scores recomputed from the saved log-sum-exp)
+//   dKV: item = (batch, head, 128-key tile), loop over 64-query sub-tiles:
+//        S^T = K Q^T, dP^T = V dO^T (SS, 128 x 64); P^T, dS^T packed fp16 in TMEM; dV += P^T dO, dK += dS^T Q (TS)
+//   dQ : item = (batch, head, 128-query tile), loop over 64-key sub-tiles:
+//        S = Q K^T, dP = dO V^T; dS packed; dQ += dS K
+// A 64-row fp16 tile is used both K-major (score MMAs) and MN-major (gradient MMAs) from one shared-memory image.
+// Packed operands: thread `half` of a row owns 32 of the 64 columns of a sub-tile and writes its 16 packed columns
+// at the start of its own 32-column range, so no thread overwrites scores another one has not loaded yet:
+// A-operand k-step k (16 contraction indices) lives at column (k >> 1) * 32 + (k & 1) * 8 of the buffer.
+// =============================================================================================
+struct BwdParams {
+  const float* lse;
+  const float* delta;
+  int N, heads, tiles128, sub64, total_items;
+  float scale;
+};
+
+__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)((k >> 1) * 32 + (k & 1) * 8); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                        const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Ks = smem;
+  uint8_t* Vs = smem + kTile128;
+  uint8_t* St = smem + 2 * kTile128;          // stage s at St + s * 2 * kTile64: [Q64 | dO64]
+  uint8_t* obox = St + 4 * kTile64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* qd_full = bars + 2;    // [2]
+  uint64_t* qd_empty = bars + 4;   // [2] two arrivals: the score MMAs and the gradient MMAs have both read the stage
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* acc_full = bars + 10;
+  uint64_t* acc_empty = bars + 11;
+  uint64_t* sfree = bars + 12;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&sfree[s], 1);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int NS = p.sub64;
+
+  if (warp == 0) {
+    uint32_t sub_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int kt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(kv_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * kTile128);
+        tma_load_3d(Ks, &tmQKV128, kv_full, inner + h * DH, kt * 128, b);
+        tma_load_3d(Vs, &tmQKV128, kv_full, 2 * inner + h * DH, kt * 128, b);
+      }
+      __syncwarp();
+      for (int i = 0; i < NS; ++i, ++sub_it) {
+        const int s = sub_it & 1;
+        const uint32_t ph = (sub_it >> 1) & 1;
+        uint8_t* st = St + s * 2 * kTile64;
+        mbar_wait(&qd_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&qd_full[s], 2 * kTile64);
+          tma_load_3d(st, &tmQKV64, &qd_full[s], h * DH, i * 64, b);
+          tma_load_3d(st + kTile64, &tmDO64, &qd_full[s], h * DH, i * 64, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- issuer A: S^T = K Q^T, dP^T = V dO^T
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
+    const uint64_t kd = kmajor_desc(Ks);
+    const uint64_t vd = kmajor_desc(Vs);
+    const uint64_t qd0 = kmajor_desc(St);
+    uint32_t sd_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(kv_full, item_it & 1);
+      for (int i = 0; i < NS; ++i, ++sd_it) {
+        const int s = sd_it & 1;
+        const uint32_t ph = (sd_it >> 1) & 1;
+        mbar_wait(&qd_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t qd = desc_advance(qd0, s * 2 * kTile64);
+          const uint64_t dd = desc_advance(qd, kTile64);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + s * 64, desc_advance(kd, k * kKStepK), desc_advance(qd, k * kKStepK), idesc_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(vd, k * kKStepK), desc_advance(dd, k * kKStepK), idesc_s, k != 0);
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&qd_empty[s]);
+          if (i == NS - 1) umma_commit<1>(kv_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: dV += P^T dO, dK += dS^T Q (A packed fp16 from TMEM, B = the stage's tiles read MN-major)
+    constexpr uint32_t idesc_g = make_idesc_f16(128, DH, 0, 1);
+    const uint64_t qm0 = mnmajor_desc(St);
+    uint32_t dv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int i = 0; i < NS; ++i, ++dv_it) {
+        const int s = dv_it & 1;
+        const uint32_t ph = (dv_it >> 1) & 1;
+        if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        mbar_wait(&qd_full[s], ph);
+        mbar_wait(&p_full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t qmd = desc_advance(qm0, s * 2 * kTile64);
+          const uint64_t dmd = desc_advance(qmd, kTile64);
+          const uint32_t acc_on = i > 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dV += P^T dO      (64 queries = 4 x UMMA_K)
+            umma_f16_ts(tmem_base + 256, tmem_base + s * 64 + packed_a_col(k), desc_advance(dmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dK += dS^T Q
+            umma_f16_ts(tmem_base + 320, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(qmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+          umma_commit<1>(&qd_empty[s]);
+          umma_commit<1>(&sfree[s]);
+          if (i == NS - 1) umma_commit<1>(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int kt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
+      const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
+      // per-column lse / delta live in one register per lane and are broadcast with shuffles (see attention_tc.cu)
+      const int qcol = half * 32 + lane;
+      float raw_l = 0.f, raw_e = 0.f;
+      bool nvalid = qcol < p.N;
+      if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it & 1;
+        const float myL = nvalid ? raw_l * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
+        const float myE = nvalid ? raw_e : 0.f;
+        {
+          const int qi = (i + 1) * 64 + qcol;
+          nvalid = i + 1 < NS && qi < p.N;
+          if (nvalid) { raw_l = lb[qi]; raw_e = eb[qi]; }
+        }
+        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+        const int col = s * 64 + half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        tmem_ld_wait();
+        uint32_t pp[16], ds[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float L0 = __shfl_sync(0xffffffffu, myL, 2 * j), L1 = __shfl_sync(0xffffffffu, myL, 2 * j + 1);
+          const float E0 = __shfl_sync(0xffffffffu, myE, 2 * j), E1 = __shfl_sync(0xffffffffu, myE, 2 * j + 1);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -L1));
+          pp[j] = pack_h2(p0, p1);
+          ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - E0), p1 * (__uint_as_float(g[2 * j + 1]) - E1));
+        }
+        tmem_st_32x16(tmem_base + lane_off + col, pp);
+        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      // item epilogue: this thread's key row of dV (half 0) or dK (half 1)
+      mbar_wait(acc_full, item_it & 1);
+      tcgen05_fence_after();
+      const int col0 = (half == 0 ? 2 * inner : inner) + h * DH;
+      const float mul = half == 0 ? 1.f : p.scale;
+#pragma unroll 1
+      for (int cc = 0; cc < DH / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_off + (half == 0 ? 256 : 320) + cc * 32, v);
+        tmem_ld_wait();
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+        store_box_h(obox + (warp - 2) * 4096, &tmOut, r, mul, col0 + cc * 32, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
+                       const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ds = smem + kTile128;
+  uint8_t* St = smem + 2 * kTile128;          // stage s at St + s * 2 * kTile64: [K64 | V64]
+  uint8_t* obox = St + 4 * kTile64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [2]
+  uint64_t* kv_empty = bars + 4;   // [2] two arrivals (score MMAs, dQ MMAs)
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* acc_full = bars + 10;
+  uint64_t* acc_empty = bars + 11;
+  uint64_t* sfree = bars + 12;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmQKV64);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&sfree[s], 1);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int NS = p.sub64;
+
+  if (warp == 0) {
+    uint32_t sub_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * kTile128);
+        tma_load_3d(Qs, &tmQKV128, q_full, h * DH, qt * 128, b);
+        tma_load_3d(Ds, &tmDO128, q_full, h * DH, qt * 128, b);
+      }
+      __syncwarp();
+      for (int i = 0; i < NS; ++i, ++sub_it) {
+        const int s = sub_it & 1;
+        const uint32_t ph = (sub_it >> 1) & 1;
+        uint8_t* st = St + s * 2 * kTile64;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[s], 2 * kTile64);
+          tma_load_3d(st, &tmQKV64, &kv_full[s], inner + h * DH, i * 64, b);
+          tma_load_3d(st + kTile64, &tmQKV64, &kv_full[s], 2 * inner + h * DH, i * 64, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- issuer A: S = Q K^T, dP = dO V^T
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
+    const uint64_t qd = kmajor_desc(Qs);
+    const uint64_t dd = kmajor_desc(Ds);
+    const uint64_t kk0 = kmajor_desc(St);
+    uint32_t sd_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      mbar_wait(q_full, item_it & 1);
+      for (int i = 0; i < NS; ++i, ++sd_it) {
+        const int s = sd_it & 1;
+        const uint32_t ph = (sd_it >> 1) & 1;
+        mbar_wait(&kv_full[s], ph);
+        mbar_wait(&sfree[s], ph ^ 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kkd = desc_advance(kk0, s * 2 * kTile64);
+          const uint64_t vkd = desc_advance(kkd, kTile64);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + s * 64, desc_advance(qd, k * kKStepK), desc_advance(kkd, k * kKStepK), idesc_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(dd, k * kKStepK), desc_advance(vkd, k * kKStepK), idesc_s, k != 0);
+          umma_commit<1>(&s_full[s]);
+          umma_commit<1>(&kv_empty[s]);
+          if (i == NS - 1) umma_commit<1>(q_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssuerB) {
+    // ---- issuer B: dQ += dS K (A packed fp16 from TMEM, B = the K sub-tile read MN-major)
+    constexpr uint32_t idesc_g = make_idesc_f16(128, DH, 0, 1);
+    const uint64_t km0 = mnmajor_desc(St);
+    uint32_t dq_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      for (int i = 0; i < NS; ++i, ++dq_it) {
+        const int s = dq_it & 1;
+        const uint32_t ph = (dq_it >> 1) & 1;
+        if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
+        mbar_wait(&kv_full[s], ph);
+        mbar_wait(&p_full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t kmd = desc_advance(km0, s * 2 * kTile64);
+          const uint32_t acc_on = i > 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tmem_base + 256, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(kmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+          umma_commit<1>(&kv_empty[s]);
+          umma_commit<1>(&sfree[s]);
+          if (i == NS - 1) umma_commit<1>(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int OC = DH / 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qt = w % p.tiles128;
+      const int bh = w / p.tiles128;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int row = qt * 128 + q * 32 + lane;
+      const long long sidx = ((long long)b * p.heads + h) * p.N + row;
+      const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
+      const float dl = row < p.N ? p.delta[sidx] : 0.f;
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it & 1;
+        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        tcgen05_fence_after();
+        const int col = s * 64 + half * 32;
+        const int kv_left = p.N - i * 64 - half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        tmem_ld_wait();
+        uint32_t ds[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
+          if (2 * j >= kv_left) p0 = 0.f;            // ragged last tile: padded key columns contribute nothing
+          if (2 * j + 1 >= kv_left) p1 = 0.f;
+          ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
+        }
+        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      mbar_wait(acc_full, item_it & 1);
+      tcgen05_fence_after();
+      {
+        uint32_t v[OC];
+        tmem_ld_32x32(tmem_base + lane_off + 256 + half * OC, v);
+        tmem_ld_wait();
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+        store_box_h(obox + (warp - 2) * 4096, &tmOut, r, p.scale, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// fp16 [B*N, ld] matrix viewed as {ld, N, B}; box {64 (one 128-byte row), rows, 1}, SWIZZLE_128B
+int make_tile_map(CUtensorMap* out, const void* ptr, long long ld, int N, int B, int box_rows) {
+  const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
+  const unsigned long long strides[2] = {(unsigned long long)ld * 2, (unsigned long long)N * ld * 2};
+  const unsigned box[3] = {64, (unsigned)box_rows, 1};
+  return make_tensor_map(out, ptr, 2, 3, dims, strides, box, 0);
+}
+// store view: 32 x 32 un-swizzled fp16 boxes
+int make_store_map(CUtensorMap* out, const void* ptr, long long ld, int N, int B) {
+  const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
+  const unsigned long long strides[2] = {(unsigned long long)ld * 2, (unsigned long long)N * ld * 2};
+  const unsigned box[3] = {32, 32, 1};
+  return make_tensor_map(out, ptr, 2, 3, dims, strides, box, 3);
+}
+
+int persistent_grid(int items) {
+  int grid = num_sms();
+  if (sm_limit() > 0 && grid > sm_limit()) grid = sm_limit();
+  return grid > items ? items : grid;
+}
+
+}  // namespace
+
+// qkv fp16 [B*N, 3*heads*64]; out fp16 [B*N, heads*64]; lse fp32 [B*heads*N]
+int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, int heads, int dh, float scale, cudaStream_t stream) {
+  B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  B200_CHECK_ARG(dh == DH, "attention_f16: dim_head must be 64 (got %d); other head sizes use the tf32 core", dh);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "attention: qkv/out must be 16-byte aligned");
+  const int inner = heads * DH;
+  CUtensorMap tmQKV, tmO;
+  int rc;
+  if ((rc = make_tile_map(&tmQKV, qkv, 3ll * inner, N, B, 128))) return rc;
+  if ((rc = make_store_map(&tmO, out, inner, N, B))) return rc;
+  FwdParams p;
+  p.lse = lse; p.N = N; p.heads = heads;
+  p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
+  p.total_items = p.q_tiles * heads * B;
+  p.scale = scale;
+  constexpr int smem = 5 * kTile128 + kBoxBytes + 512 + 3 * 256 * 4 + 1024;
+  B200_CONFIGURE_SMEM_ONCE(attn_fwd_f16_kernel, smem);
+  attn_fwd_f16_kernel<<<persistent_grid(p.total_items), kThreads, smem, stream>>>(tmQKV, tmO, p);
+  B200_LAUNCH_OK("attn_fwd_f16_kernel");
+  return 0;
+}
+
+int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
+                    cudaStream_t stream);
+
+// dout fp16 (carrying the gradient scale), out fp16; dqkv fp16 (same scale); delta scratch fp32 [B*heads*N]
+int attention_f16_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* delta, int B, int N,
+                           int heads, int dh, float scale, cudaStream_t stream) {
+  B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  B200_CHECK_ARG(dh == DH, "attention_f16: dim_head must be 64 (got %d)", dh);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "attention: qkv/dout/dqkv must be 16-byte aligned");
+  int rc = attention_delta(out, 1, dout, 1, delta, B, N, heads, dh, stream);
+  if (rc) return rc;
+  const int inner = heads * DH;
+  const long long ld = 3ll * inner;
+  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmOut;
+  if ((rc = make_tile_map(&tmQKV128, qkv, ld, N, B, 128))) return rc;
+  if ((rc = make_tile_map(&tmQKV64, qkv, ld, N, B, 64))) return rc;
+  if ((rc = make_tile_map(&tmDO128, dout, inner, N, B, 128))) return rc;
+  if ((rc = make_tile_map(&tmDO64, dout, inner, N, B, 64))) return rc;
+  if ((rc = make_store_map(&tmOut, dqkv, ld, N, B))) return rc;
+  BwdParams p;
+  p.lse = lse; p.delta = delta; p.N = N; p.heads = heads;
+  p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
+  p.total_items = p.tiles128 * heads * B;
+  p.scale = scale;
+  constexpr int smem = 2 * kTile128 + 4 * kTile64 + kBoxBytes + 256 + 1024;
+  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem);
+  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem);
+  const int grid = persistent_grid(p.total_items);
+  attn_bwd_dkv_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmQKV64, tmDO64, tmOut, p);
+  B200_LAUNCH_OK("attn_bwd_dkv_f16_kernel");
+  attn_bwd_dq_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmDO128, tmQKV64, tmOut, p);
+  B200_LAUNCH_OK("attn_bwd_dq_f16_kernel");
+  return 0;
+}
+
+}  // namespace b200

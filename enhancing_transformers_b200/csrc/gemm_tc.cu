@@ -227,13 +227,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int ew = warp - 2;
     const int ehalf = ew >> 2;
-    uint8_t* out_buf = staging + ew * 8192;
-    uint8_t* in_buf = out_buf + 4096;
+    uint8_t* const box0 = staging + ew * 8192;
+    uint8_t* in_buf = box0 + 4096;
     uint64_t* in_full = in_full_all + ew;
     const uint32_t swz = lane & 7;
     const bool tma_in = p.in_mode != 0;
     const float alpha = p.alpha_ptr ? __ldg(p.alpha_ptr) : 1.f;
-    uint32_t in_cnt = 0;
+    uint32_t in_cnt = 0, out_cnt = 0;
     constexpr int NCHUNK = BN / CW;
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
@@ -288,8 +288,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(in_buf, &tmIn, in_full, col0 + 2 * CW, row0);
           }
         }
-        // the staging buffer must have been read by the TMA store of this warp's previous chunk
-        if (lane == 0) bulk_wait_group_read<0>();
+        // Store staging: without a TMA-fed epilogue input the input box is free, so the warp alternates between two
+        // store boxes and only waits for the store *before* the previous one (its smem reads overlap this chunk's
+        // TMEM load and math); with an input box there is a single store box and the wait is for the previous store.
+        uint8_t* const out_buf = (tma_in || !(out_cnt & 1)) ? box0 : in_buf;
+        ++out_cnt;
+        if (lane == 0) { if (tma_in) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
         __syncwarp();
         uint8_t* outb = out_buf + lane * 128;
         if constexpr (OUT16 == 0) {

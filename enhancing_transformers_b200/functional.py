@@ -178,6 +178,7 @@ def _colsum_of(t: Tensor) -> Tensor:
 # parameters per block, in order: ln1_w, ln1_b, w_qkv, w_out, b_out, ln2_w, ln2_b, w1, b1, w2, b2
 # ------------------------------------------------------------------------------------------------
 LAYER_PARAMS = 11
+ATTENTION_F16 = os.environ.get("B200VQ_ATTENTION_F16", "1") != "0"   # fp16 mode: kind::f16 attention core for dim_head 64
 
 
 def f16_supported(dim: int, inner: int, mlp: int) -> bool:
@@ -254,8 +255,12 @@ def _block_fwd_f16(x, prm, dims):
     cg = GEMM_CTA_GROUP
     wq, wo, w1h, w2h = (weight_shadow(w, "f16") for w in (w_qkv, w_out, w1, w2))
     h1, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, False, out_half=True)
-    qkv = ops.gemm(h1, wq, M, 3 * inner, D, round_out=True, cta_group=cg)                 # fp32, tf32-rounded: the attention core is kind::tf32
-    o, lse = ops.attention_fwd(qkv, B, N, heads, dh, scale, False, out_half=True)
+    if dh == 64 and ATTENTION_F16:
+        qkv = ops.gemm(h1, wq, M, 3 * inner, D, out_half=True, cta_group=cg)              # fp16 qkv -> kind::f16 attention core
+        o, lse = ops.attention_f16_fwd(qkv, B, N, heads, dh, scale)
+    else:
+        qkv = ops.gemm(h1, wq, M, 3 * inner, D, round_out=True, cta_group=cg)             # fp32, tf32-rounded: kind::tf32 attention core
+        o, lse = ops.attention_fwd(qkv, B, N, heads, dh, scale, False, out_half=True)
     x1 = ops.gemm(o, wo, M, D, inner, bias=b_out, res=x, cta_group=cg)
     h2, mean2, rstd2 = ops.layernorm_fwd(x1, ln2_w, ln2_b, False, out_half=True)
     t = ops.gemm(h2, w1h, M, mlp, D, bias=b1, act=1, out_half=True, cta_group=cg)
@@ -289,10 +294,13 @@ def _block_bwd_f16(saved, prm, dims, g, g_colsum, gh, sc, need_w):
     del dh2
     # ---- attention branch
     dwo = _wgrad(g1h, o, D, inner, inv_scale=inv) if need_w else None
-    do = ops.gemm(g1h, wo, M, inner, D, b_major=1, alpha=inv, round_out=True, cta_group=cg)
-    del g1h
-    dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, False, half_scale=S)         # fp16, carries S
-    del do
+    if qkv.dtype == torch.float16:
+        do = ops.gemm(g1h, wo, M, inner, D, b_major=1, out_half=True, cta_group=cg)                # fp16, still carries S
+        dqkv = ops.attention_f16_bwd(qkv, o, lse, do, B, N, heads, dh, scale)                      # fp16, carries S
+    else:
+        do = ops.gemm(g1h, wo, M, inner, D, b_major=1, alpha=inv, round_out=True, cta_group=cg)
+        dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, False, half_scale=S)     # fp16, carries S
+    del g1h, do
     dwq = _wgrad(dqkv, h1, 3 * inner, D, inv_scale=inv) if need_w else None
     dh1 = ops.gemm(dqkv, wq, M, D, 3 * inner, b_major=1, alpha=inv, cta_group=cg)
     del dqkv

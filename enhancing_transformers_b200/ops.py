@@ -220,6 +220,26 @@ def attention_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N
     return dqkv
 
 
+def attention_f16_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float) -> Tuple[Tensor, Tensor]:
+    """fp16-operand core (dh == 64): qkv fp16 -> (out fp16, lse fp32)"""
+    _req(qkv, "qkv", _HALF)
+    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=_HALF)
+    lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_attention_f16_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, dh, scale, _stream()), "attention_f16_fwd")
+    return out, lse
+
+
+def attention_f16_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, heads: int, dh: int,
+                      scale: float) -> Tensor:
+    """dqkv fp16 from dout fp16 (dout may carry a power-of-two gradient scale; dqkv then carries the same one)"""
+    _req(qkv, "qkv", _HALF); _req(out, "out", _HALF); _req(lse, "lse"); _req(dout, "dout", _HALF)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _lib.check(_lib.lib().b200vq_attention_f16_bwd(_p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(delta), B, N, heads, dh, scale,
+                                                   _stream()), "attention_f16_bwd")
+    return dqkv
+
+
 def attention_exact_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float) -> Tuple[Tensor, Tensor]:
     _req(qkv, "qkv")
     out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=torch.float32)

@@ -108,6 +108,13 @@ int b200vq_attention_fwd(const float* qkv, void* out, int out_half, float* lse, 
 int b200vq_attention_bwd(const float* qkv, const void* out, int out_half, const float* lse, const float* dout,
                          void* dqkv, int dqkv_half, const float* dqkv_scale, float* delta, int B, int N, int heads,
                          int dh, float scale, int round_out, void* stream);
+/* fp16-operand core (dh == 64): qkv16 / out16 / dout16 / dqkv16 are fp16 matrices of the shapes above; tensor-core
+ * operands fp16 (kind::f16), scores / softmax / accumulation fp32.  dout16 carries the power-of-two gradient scale of
+ * the backward segment and dqkv16 comes out with the same scale (everything is linear in dout). */
+int b200vq_attention_f16_fwd(const void* qkv16, void* out16, float* lse, int B, int N, int heads, int dh, float scale,
+                             void* stream);
+int b200vq_attention_f16_bwd(const void* qkv16, const void* out16, const float* lse, const void* dout16, void* dqkv16,
+                             float* delta, int B, int N, int heads, int dh, float scale, void* stream);
 /* the same contract with every product in error-compensated 3xTF32 (fp32-grade; precision="parity") */
 int b200vq_attention_exact_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
                                void* stream);

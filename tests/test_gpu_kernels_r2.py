@@ -248,3 +248,39 @@ def test_vq_ffma2_codes_bit_exact_large():
         gaps = O.vq_top2_gap_f64(z.numpy()[mism], E.numpy())
         assert (gaps < 1e-6).all(), (mism.size, gaps.max())
     assert mism.size <= 4
+
+
+# --------------------------------------------------------------------------- fp16-operand attention core
+@pytest.mark.parametrize("B,N,heads", [(1, 24, 3), (2, 200, 2), (2, 1024, 4), (1, 130, 1), (3, 64, 2), (1, 1024, 12)])
+def test_attention_f16_fwd_bwd(B, N, heads):
+    dh, inner = 64, heads * 64
+    qkv = torch.randn(B * N, 3 * inner, device="cuda").to(H)
+    scale = dh ** -0.5
+    o, lse = ops.attention_f16_fwd(qkv, B, N, heads, dh, scale)
+    assert o.dtype == H
+    q, k, v = (t.reshape(B, N, heads, dh).permute(0, 2, 1, 3).double() for t in qkv.split(inner, dim=-1))
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    s = (q @ k.transpose(-1, -2)) * scale
+    oref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, inner)
+    assert relerr(o, oref.detach()) < 1.5e-3                      # fp16 P (2^-11) + fp16 output rounding
+    assert relerr(lse, torch.logsumexp(s, -1).reshape(-1).detach()) < 1e-5
+    # backward: dout carries a gradient scale; dqkv comes back with the same scale
+    do = torch.randn(B * N, inner, device="cuda") * 1e-6
+    sc = ops.grad_scale(do)
+    doh = ops.to_half(do, sc[0:1])
+    oref.backward(doh.double() * sc[1].double())
+    dqkv = ops.attention_f16_bwd(qkv, o, lse, doh, B, N, heads, dh, scale).double() * sc[1].double()
+    dref = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(B * N, inner) for t in (q, k, v)], dim=-1)
+    for i, nm in enumerate("qkv"):
+        assert relerr(dqkv[:, i * inner:(i + 1) * inner], dref[:, i * inner:(i + 1) * inner]) < 3e-3, nm
+
+
+def test_attention_f16_matches_tf32_core():
+    """same inputs through the kind::tf32 core (fp16 values are exactly representable in tf32): outputs agree to
+    fp16 rounding, i.e. the fp16 core loses nothing against the tf32 one"""
+    B, N, heads, dh = 2, 512, 3, 64
+    inner = heads * dh
+    qkv = torch.randn(B * N, 3 * inner, device="cuda").to(H)
+    o16, lse16 = ops.attention_f16_fwd(qkv, B, N, heads, dh, 0.125)
+    o32, lse32 = ops.attention_fwd(qkv.float(), B, N, heads, dh, 0.125, False)
+    assert relerr(o16, o32) < 1.5e-3 and relerr(lse16, lse32) < 1e-5

@@ -193,11 +193,19 @@ def test_baseline_config_parity_vs_fp64_oracle(name, B, mode):
     # codes bit-exact on identical z (same fp32 lookup), end-to-end agreement, audited flips
     with torch.no_grad():
         _, _, idx_same = O.vq_forward(z.detach(), E, qc.get("beta", 0.25), qc.get("use_residual", False), qc.get("num_quantizers"))
-    mism = (idx != idx_same).float().mean().item()      # torch's fp32 GEMM order vs sequential FMA: exact near-ties only
-    assert mism < 2e-4, mism
-    agree = (idx == idx64).float().mean().item()
+    ntok = idx.numel() // (idx.shape[-1] if idx.dim() == 3 else 1)
+    tok_same = (idx == idx_same).reshape(ntok, -1).all(dim=1)
+    n_mism = int((~tok_same).sum())     # torch's fp32 GEMM order vs the kernel's sequential FMA: exact fp32 near-ties only
+    assert n_mism <= max(2, ntok // 5000), n_mism
+    if n_mism:
+        bad = (~tok_same).nonzero().view(-1).cpu().numpy()
+        assert (O.vq_top2_gap_f64(z.detach().reshape(-1, 32).double().cpu().numpy()[bad], E.double().cpu().numpy()) < 2e-6).all()
+    tok_agree = (idx == idx64).reshape(ntok, -1).all(dim=1)
+    agree = tok_agree.float().mean().item()
     errs["code_agreement"] = agree
-    assert agree >= (0.9999 if not fast else 0.99), errs
+    errs["tokens_differing"] = int((~tok_agree).sum())
+    # parity mode: only exact fp32 near-ties may differ (a few tokens in thousands); fast modes: tf32-level z rounding
+    assert (errs["tokens_differing"] <= max(2, ntok // 5000)) if not fast else (agree >= 0.99), errs
     audit_flipped_codes(idx, idx64, z.detach(), z64.detach(), E)
     # decoder fed the ORACLE'S codes: the reconstruction tolerance proper
     errs["dec_on_oracle_codes"] = relmax(decode(mods, idx64), rec64.detach())
