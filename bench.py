@@ -486,7 +486,8 @@ def main():
     if "secondary" in extras:
         sec = {}
         for name, cname, b, second in (("base_rq4_B128", "base_rq4", 128, False), ("large_B32", "large", 32, False),
-                                       ("base_B128_2fwd_1bwd", "base", 128, True)):
+                                       ("base_B128_2fwd_1bwd", "base", 128, True), ("base_B32_parity_mode", "base", 32, False)):
+            etb.set_precision("parity" if name.endswith("parity_mode") else precision)
             torch.manual_seed(0)
             m2 = HotPath(CONFIGS[cname]).to(dev)
             st = make_step(m2, m2)
@@ -505,8 +506,10 @@ def main():
                              model_tflops=(4.0 if second else 3.0) * flops_per_image(CONFIGS[cname]) * b / ms / 1e9)
             del m2, st, x
             torch.cuda.empty_cache()
+        etb.set_precision(precision)
         sec["note"] = ("3 timed steps after 3 warm-ups each; base_rq4 = BASELINE config 3 (use_residual, num_quantizers=4); large_B32 = the per-GPU "
-                       "share of BASELINE config 4 (batch 256 over 8 GPUs); 2fwd_1bwd = the reference training_step shape (vitvqgan.py:101-127)")
+                       "share of BASELINE config 4 (batch 256 over 8 GPUs); 2fwd_1bwd = the reference training_step shape (vitvqgan.py:101-127); parity_mode = the 3xTF32 data path "
+                       "(etb.set_precision('parity'): reconstructions within 3e-5 of the fp64 oracle, tests/test_gpu_model.py)")
         line["secondary"] = sec
     if "eager" in extras:
         line["gpu_eager_baseline"] = gpu_eager_baseline(args.config, dev)

@@ -205,7 +205,8 @@ def test_baseline_config_parity_vs_fp64_oracle(name, B, mode):
     errs["code_agreement"] = agree
     errs["tokens_differing"] = int((~tok_agree).sum())
     # parity mode: only exact fp32 near-ties may differ (a few tokens in thousands); fast modes: tf32-level z rounding
-    assert (errs["tokens_differing"] <= max(2, ntok // 5000)) if not fast else (agree >= 0.99), errs
+    depth = idx.shape[-1] if idx.dim() == 3 else 1      # every depth is one more lookup that a near-tie can flip
+    assert (errs["tokens_differing"] <= max(2, ntok // 5000)) if not fast else (agree >= 1.0 - 0.008 * depth), errs
     audit_flipped_codes(idx, idx64, z.detach(), z64.detach(), E)
     # decoder fed the ORACLE'S codes: the reconstruction tolerance proper
     errs["dec_on_oracle_codes"] = relmax(decode(mods, idx64), rec64.detach())
@@ -320,7 +321,8 @@ def test_single_head_identity_projection_transformer():
                            sd[f"layers.{i}.1.fn.net.2.weight"], sd[f"layers.{i}.1.fn.net.2.bias"]) + h
     yr = O.layer_norm(h, sd["norm.weight"], sd["norm.bias"])
     assert relmax(y.detach().cpu(), yr.detach()) < 2e-3
-    y.sum().backward(); yr.sum().backward()
+    wsum = torch.randn(2, 24, 64)                 # (a plain .sum() of LayerNorm outputs has zero gradient)
+    (y * wsum.cuda()).sum().backward(); (yr * wsum).sum().backward()
     assert relmax(x.grad.cpu(), xr.grad) < 5e-3
 
 
