@@ -49,6 +49,8 @@ _SIGNATURES = {
     "b200vq_to_half": (c_i, [c_f, c_f, c_ll, c_f, c_f]),
     "b200vq_grad_scale_workspace_bytes": (c_sz, []),
     "b200vq_grad_scale": (c_i, [c_f, c_ll, c_i, c_f, c_f, c_sz, c_f]),
+    "b200vq_bias_act": (c_i, [c_f, c_f, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
+    "b200vq_upfirdn2d": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -90,6 +90,8 @@ int add_rows_mod(const float*, const float*, float*, long long, int, int, cudaSt
 int split_tf32_lo(const float*, float*, long long, cudaStream_t);
 int to_half(const float*, void*, long long, const float*, cudaStream_t);
 size_t grad_scale_workspace_bytes();
+int bias_act(const float*, const float*, const float*, float*, long long, int, int, int, int, float, float, cudaStream_t);
+int upfirdn2d(const float*, const float*, float*, long long, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int grad_scale(const float*, long long, int, float*, void*, size_t, cudaStream_t);
 
 }  // namespace b200
@@ -204,6 +206,15 @@ size_t b200vq_grad_scale_workspace_bytes(void) { return grad_scale_workspace_byt
 int b200vq_grad_scale(const float* g, long long n, int target_log2, float* scale2, void* workspace, size_t ws_bytes,
                       void* stream) {
   return grad_scale(g, n, target_log2, scale2, workspace, ws_bytes, S(stream));
+}
+
+int b200vq_bias_act(const float* x, const float* bias, const float* ref, float* out, long long n, int step_b, int size_b, int act,
+                    int grad, float alpha, float scale, void* stream) {
+  return bias_act(x, bias, ref, out, n, step_b, size_b, act, grad, alpha, scale, S(stream));
+}
+int b200vq_upfirdn2d(const float* in, const float* kernel, float* out, long long planes, int in_h, int in_w, int kh, int kw, int up_x,
+                     int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream) {
+  return upfirdn2d(in, kernel, out, planes, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, S(stream));
 }
 
 }  // extern "C"

@@ -163,6 +163,19 @@ size_t b200vq_grad_scale_workspace_bytes(void);
 int b200vq_grad_scale(const float* g, long long n, int target_log2, float* scale2, void* workspace, size_t ws_bytes,
                       void* stream);
 
+/* ---- the loss stage's two native ops ------------------------------------------
+ * bias_act: out = act'(x + bias[(i / step_b) % size_b], ref) * scale -- losses/op/fused_bias_act_kernel.cu:18-65.
+ *   act 1 linear / 3 leaky ReLU (slope alpha); grad 0 value, 1 first derivative applied to x (ref = forward output),
+ *   2 second derivative (zero).  bias / ref nullable.
+ * upfirdn2d: per plane [in_h, in_w]: zero-insert upsample (up), pad / crop, FIR with `kernel` [kh, kw] (true
+ *   convolution), decimate (down) -- losses/op/upfirdn2d_kernel.cu:107-207, upfirdn2d.py:168-206.
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh + down_y) / down_y, likewise out_w. */
+int b200vq_bias_act(const float* x, const float* bias, const float* ref, float* out, long long n, int step_b, int size_b,
+                    int act, int grad, float alpha, float scale, void* stream);
+int b200vq_upfirdn2d(const float* in, const float* kernel, float* out, long long planes, int in_h, int in_w, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

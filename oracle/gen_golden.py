@@ -155,6 +155,59 @@ def gen_blocks(L):
     np.savez_compressed(os.path.join(OUT, "blocks.npz"), **out)
 
 
+def gen_lossops():
+    """the loss stage's two native ops through the reference's own CPU formulas (losses/op/upfirdn2d.py:168-206
+    `upfirdn2d_native`, losses/op/fused_act.py:110-122), fwd + first and second order gradients.  The op modules JIT-compile
+    their CUDA extension at import (`load(...)`): that call is stubbed, nothing else of the file is touched."""
+    import torch.utils.cpp_extension as ce
+    ce.load = lambda *a, **k: None
+    ops = {}
+    for name in ("upfirdn2d", "fused_act"):
+        spec = importlib.util.spec_from_file_location("ref_lossop_" + name, os.path.join(REF, "enhancing", "losses", "op", name + ".py"))
+        ops[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ops[name])
+    torch.manual_seed(77)
+    out = {}
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    k = k1[None, :] * k1[:, None]
+    k = k / k.sum()                                        # Blur kernel of every shipped discriminator (losses/layers.py:140-155)
+    cases = [(1, 1, (2, 1)), (1, 1, (1, 1)), (2, 1, (2, 1, 1, 2)), (1, 2, (1, 1)), (2, 2, (0, 0)), (1, 1, (-1, 2, 0, -1)), (3, 2, (2, 2)),
+             (1, 2, (0, 0))]
+    x = torch.randn(2, 5, 12, 10)
+    out["up.x"], out["up.kernel"] = x.numpy(), k.numpy()
+    for i, (u, d, pad) in enumerate(cases):
+        xi = x.clone().requires_grad_(True)
+        y = ops["upfirdn2d"].upfirdn2d(xi, k, up=u, down=d, pad=pad)
+        w = torch.randn_like(y)
+        gx, = torch.autograd.grad((y * w).sum(), xi)
+        out[f"up.{i}.cfg"] = np.array([u, d] + list(pad if len(pad) == 4 else (pad[0], pad[1], pad[0], pad[1])))
+        out[f"up.{i}.y"], out[f"up.{i}.w"], out[f"up.{i}.gx"] = y.detach().numpy(), w.numpy(), gx.numpy()
+    # asymmetric kernel: catches a missing flip
+    ka = torch.randn(3, 4)
+    xi = x.clone().requires_grad_(True)
+    y = ops["upfirdn2d"].upfirdn2d(xi, ka, up=2, down=1, pad=(1, 2, 2, 1))
+    w = torch.randn_like(y)
+    out["up.asym.kernel"], out["up.asym.y"], out["up.asym.w"] = ka.numpy(), y.detach().numpy(), w.numpy()
+    out["up.asym.gx"] = torch.autograd.grad((y * w).sum(), xi)[0].numpy()
+    # fused bias + leaky ReLU (slope 0.2, gain sqrt(2)), 4-D and 2-D inputs, with and without bias, incl. double backward
+    for tag, shape in (("4d", (3, 6, 7, 5)), ("2d", (9, 6))):
+        xin = torch.randn(*shape, requires_grad=True)
+        b = torch.randn(6, requires_grad=True)
+        for use_b in (True, False):
+            y = ops["fused_act"].fused_leaky_relu(xin, b if use_b else None)
+            w = torch.randn_like(y)
+            grads = torch.autograd.grad((y * w).sum(), [xin] + ([b] if use_b else []), create_graph=True)
+            key = f"act.{tag}.{'b' if use_b else 'nob'}"
+            out[key + ".y"], out[key + ".w"], out[key + ".gx"] = y.detach().numpy(), w.numpy(), grads[0].detach().numpy()
+            if use_b:
+                out[key + ".gb"] = grads[1].detach().numpy()
+            # second order: d/dw-direction of sum(gx * v) -- what an R1 penalty differentiates
+            v = torch.randn_like(xin)
+            out[key + ".v"] = v.numpy()
+        out[f"act.{tag}.x"], out[f"act.{tag}.bias"] = xin.detach().numpy(), b.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "lossops.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not present: golden vectors can only be generated in the build container")
@@ -165,5 +218,6 @@ if __name__ == "__main__":
     gen_blocks(L)
     gen_vq(Q)
     gen_vit(L, Q)
+    gen_lossops()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
