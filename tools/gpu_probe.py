@@ -465,6 +465,32 @@ def g_modes():
               f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 
 
+def g_attn16():
+    """per-kernel time of the fp16 attention core vs the tf32 one (B from argv, default 64; base heads)"""
+    import sys
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+    N, heads, dh = 1024, 12, 64
+    inner = heads * dh
+    qkv32 = tf32_rn(torch.randn(B * N, 3 * inner, device="cuda"))
+    qkv16 = qkv32.half()
+    fl = 4 * B * heads * N * N * dh
+    ms = time_ms(lambda: ops.attention_fwd(qkv32, B, N, heads, dh, 0.125, True), iters=5, warm=2)
+    print(f"tf32 fwd B={B}: {ms:.3f} ms {fl/ms/1e9:.1f} TFLOP/s")
+    ms = time_ms(lambda: ops.attention_f16_fwd(qkv16, B, N, heads, dh, 0.125), iters=5, warm=2)
+    print(f"f16  fwd B={B}: {ms:.3f} ms {fl/ms/1e9:.1f} TFLOP/s")
+    o32, lse = ops.attention_fwd(qkv32, B, N, heads, dh, 0.125, True)
+    o16, lse16 = ops.attention_f16_fwd(qkv16, B, N, heads, dh, 0.125)
+    do32 = tf32_rn(torch.randn(B * N, inner, device="cuda"))
+    do16 = do32.half()
+    ms = time_ms(lambda: ops.attention_bwd(qkv32, o32, lse, do32, B, N, heads, dh, 0.125, True), iters=5, warm=2)
+    print(f"tf32 bwd B={B}: {ms:.3f} ms {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
+    ms = time_ms(lambda: ops.attention_f16_bwd(qkv16, o16, lse16, do16, B, N, heads, dh, 0.125), iters=5, warm=2)
+    print(f"f16  bwd B={B}: {ms:.3f} ms {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
+
+
 def g_attn_trace():
     """timeline of the dQ kernel's MMA warp and two softmax warps (needs B200VQ_LIB=.../libb200vq_trace.so)"""
     import ctypes
