@@ -18,15 +18,21 @@ namespace b200 {
 
 namespace {
 
-constexpr int kThreads = 352;      // warp 0 TMA, warp 1 MMA issuer A, warps 2..9 softmax (two per TMEM lane quarter), warp 10 MMA issuer B
-constexpr int kIssuerB = 10;
+// With fp16 operands the MMAs take half the issue slots and the softmax warps become the critical path (measured: the
+// 8-softmax-warp port of the tf32 kernels ran at exactly the tf32 kernels' speed).  Hence SIXTEEN softmax warps: four per
+// TMEM lane quarter, a row shared by four threads, each owning a quarter of the tile's columns -- half the serial work per
+// warp and twice the warps per scheduler to hide tcgen05.ld/st, barrier and ex2 latencies behind each other.
+constexpr int kThreads = 608;      // warp 0 TMA, warp 1 MMA issuer A, warps 2..17 softmax (four per TMEM lane quarter), warp 18 MMA issuer B
+constexpr int kIssuerB = 18;
+constexpr int kSoftmaxWarps = 16;
 constexpr int DH = 64;             // head dim: one 128-byte row of fp16
 constexpr int kTile128 = 128 * 128;   // bytes of a 128-row tile
 constexpr int kTile64 = 64 * 128;     // bytes of a 64-row tile
 constexpr float kLog2eF = 1.4426950408889634f;
-constexpr int kBoxBytes = 8 * 4096;   // one store box per softmax warp
+constexpr int kBoxBytes = kSoftmaxWarps * 2048;   // one 32-row x 64-byte store box per softmax warp
 
-__device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 2) : "memory"); }
+// named barrier of the four softmax warps that share TMEM lane quarter q (ids 2..5, 128 threads)
+__device__ __forceinline__ void quad_bar(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 2) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem], fp16 inputs: A holds M = 128 rows (lanes) x K = 16 as 8 columns of packed pairs
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -43,6 +49,10 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {      // values known to be in fp16 range
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -56,6 +66,29 @@ __device__ __forceinline__ void store_box_h(uint8_t* box, const CUtensorMap* tm,
   uint8_t* rowp = box + lane * 64;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    pk.x = pack_half2_sat(r[8 * j] * mul, r[8 * j + 1] * mul);
+    pk.y = pack_half2_sat(r[8 * j + 2] * mul, r[8 * j + 3] * mul);
+    pk.z = pack_half2_sat(r[8 * j + 4] * mul, r[8 * j + 5] * mul);
+    pk.w = pack_half2_sat(r[8 * j + 6] * mul, r[8 * j + 7] * mul);
+    *reinterpret_cast<uint4*>(rowp + j * 16) = pk;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, box, c0, c1, c2);
+    bulk_commit_group();
+  }
+}
+
+// 32 rows x 16 values -> 32-row x 32-byte box
+__device__ __forceinline__ void store_box_h16(uint8_t* box, const CUtensorMap* tm, const float (&r)[16], float mul, int c0, int c1, int c2,
+                                              int lane) {
+  if (lane == 0) bulk_wait_group_read<0>();
+  __syncwarp();
+  uint8_t* rowp = box + lane * 32;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
     uint4 pk;
     pk.x = pack_half2_sat(r[8 * j] * mul, r[8 * j + 1] * mul);
     pk.y = pack_half2_sat(r[8 * j + 2] * mul, r[8 * j + 3] * mul);
@@ -109,7 +142,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* o_empty = bars + 16;  // [2]
   uint64_t* sfree = bars + 18;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* xch = reinterpret_cast<float*>(bars + 22);   // [3][2][128] row-max (double buffered) and row-sum exchange
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [2][4][128] row-max (double buffered) + [4][128] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -119,8 +152,8 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
-      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
     fence_barrier_init();
@@ -214,10 +247,12 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
     }
   } else {
-    // ---- softmax / output warps (see attention_tc.cu for the commentary; identical structure)
+    // ---- softmax / output warps: a query row (TMEM lane) is shared by four threads (warps of the same lane quarter),
+    // each owning 32 of the tile's 128 scores and 16 of the 64 output columns; the row max (per tile) and the row sum
+    // (once per item) are exchanged through shared memory under a 128-thread named barrier.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int OC = DH / 2;
+    const int sub = (warp - 2) >> 2;
+    constexpr int OC = DH / 4;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const float c = p.scale * kLog2eF;
@@ -233,7 +268,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       auto fold_pv = [&](uint32_t it, float alpha) {
         const int sp = it & 1;
         uint32_t v[OC];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + sp * 64 + half * OC, v);
+        tmem_ld_32x16(tmem_base + lane_off + 256 + sp * 64 + sub * OC, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
@@ -241,49 +276,40 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[sp]);
       };
-      uint32_t v0[32], v1[32];
+      uint32_t v0[32];
       mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
       tcgen05_fence_after();
-      {
-        const uint32_t s0 = tmem_base + lane_off + (t_it & 1) * 128 + half * 64;
-        tmem_ld_32x32(s0, v0);
-        tmem_ld_32x32(s0 + 32, v1);
-      }
+      tmem_ld_32x32(tmem_base + lane_off + (t_it & 1) * 128 + sub * 32, v0);
       tmem_ld_wait();
       for (int j = 0; j < T; ++j, ++t_it) {
         const int s = t_it & 1;
-        const int kv_left = p.N - j * 128 - half * 64;
-        if (kv_left < 64) {
+        const int kv_left = p.N - j * 128 - sub * 32;       // this thread's columns >= kv_left are padding
+        if (kv_left < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_left) v0[i] = 0xff800000u;
-            if (32 + i >= kv_left) v1[i] = 0xff800000u;
-          }
+          for (int i = 0; i < 32; ++i)
+            if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
         }
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        float* xs = xch + (t_it & 1) * 256;
-        xs[half * 128 + row_in_tile] = mx;
-        pair_bar(q);        // also orders the partner's S loads before this thread's packed P stores (they overlap its columns)
-        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v0[i]));
+        float* xs = xch + (t_it & 1) * 512;
+        xs[sub * 128 + row_in_tile] = mx;
+        quad_bar(q);        // also orders the partners' S loads before this thread's packed P stores (they overlap their columns)
+        mx = fmaxf(fmaxf(xs[row_in_tile], xs[128 + row_in_tile]), fmaxf(xs[256 + row_in_tile], xs[384 + row_in_tile]));
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
         float sum = 0.f, sum1 = 0.f;
-        uint32_t pk[32];       // this thread's 64 probabilities as 32 packed fp16 pairs (keys half*64 + 2i, +1)
+        uint32_t pk[16];       // this thread's 32 probabilities as 16 packed fp16 pairs (keys sub*32 + 2i, +1)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a0 = ex2_approx(fmaf(__uint_as_float(v0[2 * i]), c, -mc));
           const float a1 = ex2_approx(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc));
-          const float b0 = ex2_approx(fmaf(__uint_as_float(v1[2 * i]), c, -mc));
-          const float b1 = ex2_approx(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc));
-          sum += a0 + a1; sum1 += b0 + b1;
+          sum += a0; sum1 += a1;
           pk[i] = pack_h2(a0, a1);
-          pk[16 + i] = pack_h2(b0, b1);
         }
         sum += sum1;
-        tmem_st_32x32(tmem_base + lane_off + s * 128 + half * 32, pk);     // P columns [0,64) of the S buffer
+        tmem_st_32x16(tmem_base + lane_off + s * 128 + sub * 16, pk);     // P columns [0,64) of the S buffer
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -295,11 +321,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         else if (more)      mbar_wait(&s_full[s ^ 1], ph_s);
         else if (j >= 1)    mbar_wait(&o_full[s ^ 1], ph_o);
         tcgen05_fence_after();
-        if (more) {
-          const uint32_t sn = tmem_base + lane_off + (s ^ 1) * 128 + half * 64;
-          tmem_ld_32x32(sn, v0);
-          tmem_ld_32x32(sn + 32, v1);
-        }
+        if (more) tmem_ld_32x32(tmem_base + lane_off + (s ^ 1) * 128 + sub * 32, v0);
         if (j >= 1) fold_pv(t_it - 1, alpha_prev);
         else        tmem_ld_wait();
         alpha_prev = alpha;
@@ -308,14 +330,14 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
       tcgen05_fence_after();
       fold_pv(t_it - 1, alpha_prev);
-      float* ls = xch + 512;
-      ls[half * 128 + row_in_tile] = l;
-      pair_bar(q);
-      l += ls[(half ^ 1) * 128 + row_in_tile];
+      float* ls = xch + 1024;
+      ls[sub * 128 + row_in_tile] = l;
+      quad_bar(q);
+      l = (ls[row_in_tile] + ls[128 + row_in_tile]) + (ls[256 + row_in_tile] + ls[384 + row_in_tile]);
       const int row = qt * 128 + row_in_tile;
-      store_box_h(obox + (warp - 2) * 4096, &tmO, o, 1.f / l, h * DH + half * OC, qt * 128 + q * 32, b, lane);
-      if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
-      pair_bar(q);
+      store_box_h16(obox + (warp - 2) * 2048, &tmO, o, 1.f / l, h * DH + sub * OC, qt * 128 + q * 32, b, lane);
+      if (row < p.N && sub == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
+      quad_bar(q);     // ls is rewritten by the next item only after every partner has read it
     }
     if (lane == 0) bulk_wait_group_read<0>();
   }
@@ -334,9 +356,9 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 //   dQ : item = (batch, head, 128-query tile), loop over 64-key sub-tiles:
 //        S = Q K^T, dP = dO V^T; dS packed; dQ += dS K
 // A 64-row fp16 tile is used both K-major (score MMAs) and MN-major (gradient MMAs) from one shared-memory image.
-// Packed operands: thread `half` of a row owns 32 of the 64 columns of a sub-tile and writes its 16 packed columns
-// at the start of its own 32-column range, so no thread overwrites scores another one has not loaded yet:
-// A-operand k-step k (16 contraction indices) lives at column (k >> 1) * 32 + (k & 1) * 8 of the buffer.
+// Packed operands: thread `sub` (0..3) of a row owns 16 of the 64 columns of a sub-tile and writes its 8 packed columns
+// at the start of its own 16-column range, so no thread overwrites scores another one has not loaded yet:
+// A-operand k-step k (16 contraction indices = thread k's columns) lives at column k * 16 of the buffer.
 // =============================================================================================
 struct BwdParams {
   const float* lse;
@@ -345,7 +367,7 @@ struct BwdParams {
   float scale;
 };
 
-__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)((k >> 1) * 32 + (k & 1) * 8); }
+__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)(k * 16); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
@@ -374,10 +396,10 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -476,8 +498,10 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
     }
   } else {
+    // 16 softmax warps: the four warps of a TMEM lane quarter (key rows) split the 64 query columns of a sub-tile;
+    // at the end of an item warps sub 0,1 store dV (32 columns each), warps sub 2,3 store dK.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
@@ -487,8 +511,9 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // per-column lse / delta live in one register per lane and are broadcast with shuffles (see attention_tc.cu)
-      const int qcol = half * 32 + lane;
+      // per-column lse / delta: lane l keeps the values of query column sub*16 + (l & 15) of the current sub-tile in
+      // registers (fetched one sub-tile ahead) and the 16 columns are broadcast with warp shuffles (see attention_tc.cu)
+      const int qcol = sub * 16 + (lane & 15);
       float raw_l = 0.f, raw_e = 0.f;
       bool nvalid = qcol < p.N;
       if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
@@ -503,14 +528,14 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         }
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-        const int col = s * 64 + half * 32;
-        uint32_t v[32], g[32];
-        tmem_ld_32x32(tmem_base + lane_off + col, v);
-        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        const int col = s * 64 + sub * 16;
+        uint32_t v[16], g[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, v);
+        tmem_ld_32x16(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        uint32_t pp[16], ds[16];
+        uint32_t pp[8], ds[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float L0 = __shfl_sync(0xffffffffu, myL, 2 * j), L1 = __shfl_sync(0xffffffffu, myL, 2 * j + 1);
           const float E0 = __shfl_sync(0xffffffffu, myE, 2 * j), E1 = __shfl_sync(0xffffffffu, myE, 2 * j + 1);
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
@@ -518,27 +543,25 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           pp[j] = pack_h2(p0, p1);
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - E0), p1 * (__uint_as_float(g[2 * j + 1]) - E1));
         }
-        tmem_st_32x16(tmem_base + lane_off + col, pp);
-        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x8(tmem_base + lane_off + col, pp);
+        tmem_st_32x8(tmem_base + lane_off + 128 + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
       }
-      // item epilogue: this thread's key row of dV (half 0) or dK (half 1)
+      // item epilogue: dV lives in TMEM columns [256,320), dK in [320,384): warp `sub` takes columns 256 + sub*32
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
-      const int col0 = (half == 0 ? 2 * inner : inner) + h * DH;
-      const float mul = half == 0 ? 1.f : p.scale;
-#pragma unroll 1
-      for (int cc = 0; cc < DH / 32; ++cc) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_off + (half == 0 ? 256 : 320) + cc * 32, v);
+        tmem_ld_32x32(tmem_base + lane_off + 256 + sub * 32, v);
         tmem_ld_wait();
         float r[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-        store_box_h(obox + (warp - 2) * 4096, &tmOut, r, mul, col0 + cc * 32, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
+        const int col0 = (sub < 2 ? 2 * inner : inner) + h * DH + (sub & 1) * 32;
+        store_box_h(obox + (warp - 2) * 2048, &tmOut, r, sub < 2 ? 1.f : p.scale, col0, kt * 128 + q * 32, b, lane);   // key rows >= N are clipped
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -556,7 +579,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
-                       const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
+                       const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
@@ -581,10 +604,10 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -679,9 +702,11 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       }
     }
   } else {
+    // 16 softmax warps: thread = query row, the four warps of a lane quarter split the 64 key columns of a sub-tile
+    // and, at the end of an item, the 64 columns of dQ
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int OC = DH / 2;
+    const int sub = (warp - 2) >> 2;
+    constexpr int OC = DH / 4;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
@@ -697,22 +722,22 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         const int s = t_it & 1;
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
-        const int col = s * 64 + half * 32;
-        const int kv_left = p.N - i * 64 - half * 32;
-        uint32_t v[32], g[32];
-        tmem_ld_32x32(tmem_base + lane_off + col, v);
-        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        const int col = s * 64 + sub * 16;
+        const int kv_left = p.N - i * 64 - sub * 16;
+        uint32_t v[16], g[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, v);
+        tmem_ld_32x16(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        uint32_t ds[16];
+        uint32_t ds[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
           float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
           if (2 * j >= kv_left) p0 = 0.f;            // ragged last tile: padded key columns contribute nothing
           if (2 * j + 1 >= kv_left) p1 = 0.f;
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
         }
-        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x8(tmem_base + lane_off + 128 + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -722,12 +747,12 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       tcgen05_fence_after();
       {
         uint32_t v[OC];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + half * OC, v);
+        tmem_ld_32x16(tmem_base + lane_off + 256 + sub * OC, v);
         tmem_ld_wait();
-        float r[32];
+        float r[OC];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-        store_box_h(obox + (warp - 2) * 4096, &tmOut, r, p.scale, h * DH + half * OC, qt * 128 + q * 32, b, lane);
+        for (int j = 0; j < OC; ++j) r[j] = __uint_as_float(v[j]);
+        store_box_h16(obox + (warp - 2) * 2048, &tmOut16, r, p.scale, h * DH + sub * OC, qt * 128 + q * 32, b, lane);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -750,11 +775,11 @@ int make_tile_map(CUtensorMap* out, const void* ptr, long long ld, int N, int B,
   const unsigned box[3] = {64, (unsigned)box_rows, 1};
   return make_tensor_map(out, ptr, 2, 3, dims, strides, box, 0);
 }
-// store view: 32 x 32 un-swizzled fp16 boxes
-int make_store_map(CUtensorMap* out, const void* ptr, long long ld, int N, int B) {
+// store view: 32-row x `cols`-column un-swizzled fp16 boxes
+int make_store_map(CUtensorMap* out, const void* ptr, long long ld, int N, int B, int cols) {
   const unsigned long long dims[3] = {(unsigned long long)ld, (unsigned long long)N, (unsigned long long)B};
   const unsigned long long strides[2] = {(unsigned long long)ld * 2, (unsigned long long)N * ld * 2};
-  const unsigned box[3] = {32, 32, 1};
+  const unsigned box[3] = {(unsigned)cols, 32, 1};
   return make_tensor_map(out, ptr, 2, 3, dims, strides, box, 3);
 }
 
@@ -776,13 +801,13 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   CUtensorMap tmQKV, tmO;
   int rc;
   if ((rc = make_tile_map(&tmQKV, qkv, 3ll * inner, N, B, 128))) return rc;
-  if ((rc = make_store_map(&tmO, out, inner, N, B))) return rc;
+  if ((rc = make_store_map(&tmO, out, inner, N, B, 16))) return rc;
   FwdParams p;
   p.lse = lse; p.N = N; p.heads = heads;
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale;
-  constexpr int smem = 5 * kTile128 + kBoxBytes + 512 + 3 * 256 * 4 + 1024;
+  constexpr int smem = 5 * kTile128 + kBoxBytes + 512 + 1536 * 4 + 1024;
   B200_CONFIGURE_SMEM_ONCE(attn_fwd_f16_kernel, smem);
   attn_fwd_f16_kernel<<<persistent_grid(p.total_items), kThreads, smem, stream>>>(tmQKV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_f16_kernel");
@@ -803,12 +828,13 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   if (rc) return rc;
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
-  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmOut;
+  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmOut, tmOut16;
   if ((rc = make_tile_map(&tmQKV128, qkv, ld, N, B, 128))) return rc;
   if ((rc = make_tile_map(&tmQKV64, qkv, ld, N, B, 64))) return rc;
   if ((rc = make_tile_map(&tmDO128, dout, inner, N, B, 128))) return rc;
   if ((rc = make_tile_map(&tmDO64, dout, inner, N, B, 64))) return rc;
-  if ((rc = make_store_map(&tmOut, dqkv, ld, N, B))) return rc;
+  if ((rc = make_store_map(&tmOut, dqkv, ld, N, B, 32))) return rc;
+  if ((rc = make_store_map(&tmOut16, dqkv, ld, N, B, 16))) return rc;
   BwdParams p;
   p.lse = lse; p.delta = delta; p.N = N; p.heads = heads;
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
@@ -820,7 +846,7 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   const int grid = persistent_grid(p.total_items);
   attn_bwd_dkv_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmQKV64, tmDO64, tmOut, p);
   B200_LAUNCH_OK("attn_bwd_dkv_f16_kernel");
-  attn_bwd_dq_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmDO128, tmQKV64, tmOut, p);
+  attn_bwd_dq_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmDO128, tmQKV64, tmOut16, p);
   B200_LAUNCH_OK("attn_bwd_dq_f16_kernel");
   return 0;
 }

@@ -148,7 +148,7 @@ def test_against_oracle_shared_state_dict(name, B, mode):
         mod, _, pname = k.partition(".")
         p = dict(mods[mod].named_parameters())[pname]
         rel = ((p.grad.cpu() - v.grad).norm() / v.grad.norm()).item()
-        assert rel < (2e-2 if agree < 1.0 else GRAD_TOL[mode]), (k, rel)
+        assert rel < (5e-2 if agree < 1.0 else GRAD_TOL[mode]), (k, rel)      # a flipped code is a different decoder input
 
 
 # ------------------------------------------------------------------------------------------------
