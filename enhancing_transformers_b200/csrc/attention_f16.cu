@@ -30,6 +30,11 @@ constexpr int kTile128 = 128 * 128;   // bytes of a 128-row tile
 constexpr int kTile64 = 64 * 128;     // bytes of a 64-row tile
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr int kBoxBytes = kSoftmaxWarps * 2048;   // one 32-row x 64-byte store box per softmax warp
+// Shared-memory rings.  The loop-carried tiles are small in fp16 (16 KB per 128 rows), so the rings are deep enough to
+// cover a full TMA round trip (~1500 cycles from "stage free" to "bytes landed"): with the 2-deep rings inherited from
+// the tf32 kernels every sub-tile waited for its own load (ncu: the softmax warps' top stall is the wait for S).
+constexpr int kFwdStages = 4;      // K and V rings of the forward kernel (128-row tiles)
+constexpr int kBwdStages = 4;      // [Q64 | dO64] / [K64 | V64] rings of the backward kernels
 
 // named barrier of the four softmax warps that share TMEM lane quarter q (ids 2..5, 128 threads)
 __device__ __forceinline__ void quad_bar(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 2) : "memory"); }
@@ -125,33 +130,35 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ks = smem + kTile128;            // [2]
-  uint8_t* Vs = smem + 3 * kTile128;        // [2]
-  uint8_t* obox = smem + 5 * kTile128;
+  constexpr int NST = kFwdStages;
+  uint8_t* Qs = smem;                              // [2]: the next item's Q tile loads while this item computes
+  uint8_t* Ks = smem + 2 * kTile128;               // [NST]
+  uint8_t* Vs = smem + (2 + NST) * kTile128;       // [NST]
+  uint8_t* obox = smem + (2 + 2 * NST) * kTile128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* s_full = bars + 10;   // [2]
-  uint64_t* p_full = bars + 12;   // [2]
-  uint64_t* o_full = bars + 14;   // [2]
-  uint64_t* o_empty = bars + 16;  // [2]
-  uint64_t* sfree = bars + 18;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* xch = reinterpret_cast<float*>(bars + 22);   // [2][4][128] row-max (double buffered) + [4][128] row-sum exchange
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;    // [2]
+  uint64_t* p_full = bars + 6;    // [2]
+  uint64_t* o_full = bars + 8;    // [2]
+  uint64_t* o_empty = bars + 10;  // [2]
+  uint64_t* sfree = bars + 12;    // [2]
+  uint64_t* k_full = bars + 14;             // [NST]
+  uint64_t* k_empty = k_full + NST;         // [NST]
+  uint64_t* v_full = k_full + 2 * NST;      // [NST]
+  uint64_t* v_empty = k_full + 3 * NST;     // [NST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_full + 4 * NST);
+  float* xch = reinterpret_cast<float*>(k_full + 4 * NST + 2);   // [2][4][128] row-max (double buffered) + [4][128] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
       mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
@@ -172,15 +179,16 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      const int qs = item_it & 1;
+      mbar_wait(&q_empty[qs], ((item_it >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, kTile128);
-        tma_load_3d(Qs, &tmQKV, q_full, h * DH, qt * 128, b);
+        mbar_arrive_expect_tx(&q_full[qs], kTile128);
+        tma_load_3d(Qs + qs * kTile128, &tmQKV, &q_full[qs], h * DH, qt * 128, b);
       }
       __syncwarp();
       for (int j = 0; j < T; ++j, ++kv_it) {
-        const int s = kv_it & 1;
-        const uint32_t ph = (kv_it >> 1) & 1;
+        const int s = kv_it % NST;
+        const uint32_t ph = (kv_it / NST) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[s], kTile128);
@@ -198,25 +206,28 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   } else if (warp == 1) {
     // ---- issuer A: S_j = Q K_j^T
     constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
-    const uint64_t qd = kmajor_desc(Qs);
+    const uint64_t qd0 = kmajor_desc(Qs);
     const uint64_t kd0 = kmajor_desc(Ks);
     uint32_t s_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(q_full, item_it & 1);
+      const int qs = item_it & 1;
+      mbar_wait(&q_full[qs], (item_it >> 1) & 1);
+      const uint64_t qd = desc_advance(qd0, qs * kTile128);
       for (int j = 0; j < T; ++j, ++s_it) {
-        const int s = s_it & 1;
+        const int s = s_it & 1;                       // TMEM S buffer
         const uint32_t ph = (s_it >> 1) & 1;
-        mbar_wait(&k_full[s], ph);
+        const int r = s_it % NST;                     // K ring stage
+        mbar_wait(&k_full[r], (s_it / NST) & 1);
         mbar_wait(&sfree[s], ph ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t kd = desc_advance(kd0, s * kTile128);
+          const uint64_t kd = desc_advance(kd0, r * kTile128);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
             umma_f16<1>(tmem_base + s * 128, desc_advance(qd, k * kKStepK), desc_advance(kd, k * kKStepK), idesc_s, k != 0);
           umma_commit<1>(&s_full[s]);
-          umma_commit<1>(&k_empty[s]);
-          if (j == T - 1) umma_commit<1>(q_empty);
+          umma_commit<1>(&k_empty[r]);
+          if (j == T - 1) umma_commit<1>(&q_empty[qs]);
         }
         __syncwarp();
       }
@@ -230,17 +241,18 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int j = 0; j < T; ++j, ++pv_it) {
         const int s = pv_it & 1;
         const uint32_t ph = (pv_it >> 1) & 1;
-        mbar_wait(&v_full[s], ph);
+        const int r = pv_it % NST;                    // V ring stage
+        mbar_wait(&v_full[r], (pv_it / NST) & 1);
         mbar_wait(&o_empty[s], ph ^ 1);
         mbar_wait(&p_full[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t vd = desc_advance(vd0, s * kTile128);
+          const uint64_t vd = desc_advance(vd0, r * kTile128);
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // 128 keys = 8 x UMMA_K
             umma_f16_ts(tmem_base + 256 + s * 64, tmem_base + s * 128 + k * 8, desc_advance(vd, k * kKStepMN), idesc_o, k != 0);
           umma_commit<1>(&o_full[s]);
-          umma_commit<1>(&v_empty[s]);
+          umma_commit<1>(&v_empty[r]);
           umma_commit<1>(&sfree[s]);
         }
         __syncwarp();
@@ -374,28 +386,28 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
                         const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ks = smem;
-  uint8_t* Vs = smem + kTile128;
-  uint8_t* St = smem + 2 * kTile128;          // stage s at St + s * 2 * kTile64: [Q64 | dO64]
-  uint8_t* obox = St + 4 * kTile64;
+  constexpr int NST = kBwdStages;
+  uint8_t* KVs = smem;                        // [2] item buffers [K128 | V128]: the next item's tiles load while this one computes
+  uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [Q64 | dO64]
+  uint8_t* obox = St + NST * 2 * kTile64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* kv_empty = bars + 1;
-  uint64_t* qd_full = bars + 2;    // [2]
-  uint64_t* qd_empty = bars + 4;   // [2] two arrivals: the score MMAs and the gradient MMAs have both read the stage
-  uint64_t* s_full = bars + 6;     // [2]
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* acc_full = bars + 10;
-  uint64_t* acc_empty = bars + 11;
-  uint64_t* sfree = bars + 12;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 0;    // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;     // [2]
+  uint64_t* p_full = bars + 6;     // [2]
+  uint64_t* acc_full = bars + 8;
+  uint64_t* acc_empty = bars + 9;
+  uint64_t* sfree = bars + 10;     // [2]
+  uint64_t* qd_full = bars + 12;          // [NST]
+  uint64_t* qd_empty = qd_full + NST;     // [NST] two arrivals: the score MMAs and the gradient MMAs have both read the stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qd_full + 2 * NST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
-    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2);
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
@@ -416,16 +428,17 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const int kt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(kv_empty, (item_it & 1) ^ 1);
+      const int ib = item_it & 1;
+      mbar_wait(&kv_empty[ib], ((item_it >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(kv_full, 2 * kTile128);
-        tma_load_3d(Ks, &tmQKV128, kv_full, inner + h * DH, kt * 128, b);
-        tma_load_3d(Vs, &tmQKV128, kv_full, 2 * inner + h * DH, kt * 128, b);
+        mbar_arrive_expect_tx(&kv_full[ib], 2 * kTile128);
+        tma_load_3d(KVs + ib * 2 * kTile128, &tmQKV128, &kv_full[ib], inner + h * DH, kt * 128, b);
+        tma_load_3d(KVs + ib * 2 * kTile128 + kTile128, &tmQKV128, &kv_full[ib], 2 * inner + h * DH, kt * 128, b);
       }
       __syncwarp();
       for (int i = 0; i < NS; ++i, ++sub_it) {
-        const int s = sub_it & 1;
-        const uint32_t ph = (sub_it >> 1) & 1;
+        const int s = sub_it % NST;
+        const uint32_t ph = (sub_it / NST) & 1;
         uint8_t* st = St + s * 2 * kTile64;
         mbar_wait(&qd_empty[s], ph ^ 1);
         if (elect_one()) {
@@ -439,20 +452,23 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   } else if (warp == 1) {
     // ---- issuer A: S^T = K Q^T, dP^T = V dO^T
     constexpr uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
-    const uint64_t kd = kmajor_desc(Ks);
-    const uint64_t vd = kmajor_desc(Vs);
+    const uint64_t kd0 = kmajor_desc(KVs);
     const uint64_t qd0 = kmajor_desc(St);
     uint32_t sd_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(kv_full, item_it & 1);
+      const int ib = item_it & 1;
+      mbar_wait(&kv_full[ib], (item_it >> 1) & 1);
+      const uint64_t kd = desc_advance(kd0, ib * 2 * kTile128);
+      const uint64_t vd = desc_advance(kd, kTile128);
       for (int i = 0; i < NS; ++i, ++sd_it) {
-        const int s = sd_it & 1;
+        const int s = sd_it & 1;                      // TMEM S^T / dP^T buffer
         const uint32_t ph = (sd_it >> 1) & 1;
-        mbar_wait(&qd_full[s], ph);
+        const int r = sd_it % NST;                    // ring stage
+        mbar_wait(&qd_full[r], (sd_it / NST) & 1);
         mbar_wait(&sfree[s], ph ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t qd = desc_advance(qd0, s * 2 * kTile64);
+          const uint64_t qd = desc_advance(qd0, r * 2 * kTile64);
           const uint64_t dd = desc_advance(qd, kTile64);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
@@ -461,8 +477,8 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           for (int k = 0; k < DH / 16; ++k)
             umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(vd, k * kKStepK), desc_advance(dd, k * kKStepK), idesc_s, k != 0);
           umma_commit<1>(&s_full[s]);
-          umma_commit<1>(&qd_empty[s]);
-          if (i == NS - 1) umma_commit<1>(kv_empty);
+          umma_commit<1>(&qd_empty[r]);
+          if (i == NS - 1) umma_commit<1>(&kv_empty[ib]);
         }
         __syncwarp();
       }
@@ -476,12 +492,13 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       for (int i = 0; i < NS; ++i, ++dv_it) {
         const int s = dv_it & 1;
         const uint32_t ph = (dv_it >> 1) & 1;
+        const int r = dv_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        mbar_wait(&qd_full[s], ph);
+        mbar_wait(&qd_full[r], (dv_it / NST) & 1);
         mbar_wait(&p_full[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t qmd = desc_advance(qm0, s * 2 * kTile64);
+          const uint64_t qmd = desc_advance(qm0, r * 2 * kTile64);
           const uint64_t dmd = desc_advance(qmd, kTile64);
           const uint32_t acc_on = i > 0;
 #pragma unroll
@@ -490,7 +507,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // dK += dS^T Q
             umma_f16_ts(tmem_base + 320, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(qmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
-          umma_commit<1>(&qd_empty[s]);
+          umma_commit<1>(&qd_empty[r]);
           umma_commit<1>(&sfree[s]);
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
@@ -582,28 +599,28 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
                        const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ds = smem + kTile128;
-  uint8_t* St = smem + 2 * kTile128;          // stage s at St + s * 2 * kTile64: [K64 | V64]
-  uint8_t* obox = St + 4 * kTile64;
+  constexpr int NST = kBwdStages;
+  uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128]
+  uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [K64 | V64]
+  uint8_t* obox = St + NST * 2 * kTile64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [2]
-  uint64_t* kv_empty = bars + 4;   // [2] two arrivals (score MMAs, dQ MMAs)
-  uint64_t* s_full = bars + 6;     // [2]
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* acc_full = bars + 10;
-  uint64_t* acc_empty = bars + 11;
-  uint64_t* sfree = bars + 12;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* s_full = bars + 4;     // [2]
+  uint64_t* p_full = bars + 6;     // [2]
+  uint64_t* acc_full = bars + 8;
+  uint64_t* acc_empty = bars + 9;
+  uint64_t* sfree = bars + 10;     // [2]
+  uint64_t* kv_full = bars + 12;          // [NST]
+  uint64_t* kv_empty = kv_full + NST;     // [NST] two arrivals (score MMAs, dQ MMAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_full + 2 * NST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmQKV64);
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2);
+      mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
@@ -624,16 +641,17 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const int qt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
-      mbar_wait(q_empty, (item_it & 1) ^ 1);
+      const int ib = item_it & 1;
+      mbar_wait(&q_empty[ib], ((item_it >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, 2 * kTile128);
-        tma_load_3d(Qs, &tmQKV128, q_full, h * DH, qt * 128, b);
-        tma_load_3d(Ds, &tmDO128, q_full, h * DH, qt * 128, b);
+        mbar_arrive_expect_tx(&q_full[ib], 2 * kTile128);
+        tma_load_3d(QDs + ib * 2 * kTile128, &tmQKV128, &q_full[ib], h * DH, qt * 128, b);
+        tma_load_3d(QDs + ib * 2 * kTile128 + kTile128, &tmDO128, &q_full[ib], h * DH, qt * 128, b);
       }
       __syncwarp();
       for (int i = 0; i < NS; ++i, ++sub_it) {
-        const int s = sub_it & 1;
-        const uint32_t ph = (sub_it >> 1) & 1;
+        const int s = sub_it % NST;
+        const uint32_t ph = (sub_it / NST) & 1;
         uint8_t* st = St + s * 2 * kTile64;
         mbar_wait(&kv_empty[s], ph ^ 1);
         if (elect_one()) {
@@ -647,20 +665,23 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   } else if (warp == 1) {
     // ---- issuer A: S = Q K^T, dP = dO V^T
     constexpr uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
-    const uint64_t qd = kmajor_desc(Qs);
-    const uint64_t dd = kmajor_desc(Ds);
+    const uint64_t qd0 = kmajor_desc(QDs);
     const uint64_t kk0 = kmajor_desc(St);
     uint32_t sd_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
-      mbar_wait(q_full, item_it & 1);
+      const int ib = item_it & 1;
+      mbar_wait(&q_full[ib], (item_it >> 1) & 1);
+      const uint64_t qd = desc_advance(qd0, ib * 2 * kTile128);
+      const uint64_t dd = desc_advance(qd, kTile128);
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
         const uint32_t ph = (sd_it >> 1) & 1;
-        mbar_wait(&kv_full[s], ph);
+        const int r = sd_it % NST;
+        mbar_wait(&kv_full[r], (sd_it / NST) & 1);
         mbar_wait(&sfree[s], ph ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t kkd = desc_advance(kk0, s * 2 * kTile64);
+          const uint64_t kkd = desc_advance(kk0, r * 2 * kTile64);
           const uint64_t vkd = desc_advance(kkd, kTile64);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
@@ -669,8 +690,8 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           for (int k = 0; k < DH / 16; ++k)
             umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(dd, k * kKStepK), desc_advance(vkd, k * kKStepK), idesc_s, k != 0);
           umma_commit<1>(&s_full[s]);
-          umma_commit<1>(&kv_empty[s]);
-          if (i == NS - 1) umma_commit<1>(q_empty);
+          umma_commit<1>(&kv_empty[r]);
+          if (i == NS - 1) umma_commit<1>(&q_empty[ib]);
         }
         __syncwarp();
       }
@@ -684,17 +705,18 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       for (int i = 0; i < NS; ++i, ++dq_it) {
         const int s = dq_it & 1;
         const uint32_t ph = (dq_it >> 1) & 1;
+        const int r = dq_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        mbar_wait(&kv_full[s], ph);
+        mbar_wait(&kv_full[r], (dq_it / NST) & 1);
         mbar_wait(&p_full[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t kmd = desc_advance(km0, s * 2 * kTile64);
+          const uint64_t kmd = desc_advance(km0, r * 2 * kTile64);
           const uint32_t acc_on = i > 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16_ts(tmem_base + 256, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(kmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
-          umma_commit<1>(&kv_empty[s]);
+          umma_commit<1>(&kv_empty[r]);
           umma_commit<1>(&sfree[s]);
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
@@ -807,7 +829,7 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale;
-  constexpr int smem = 5 * kTile128 + kBoxBytes + 512 + 1536 * 4 + 1024;
+  constexpr int smem = (2 + 2 * kFwdStages) * kTile128 + kBoxBytes + 512 + 1536 * 4 + 1024;
   B200_CONFIGURE_SMEM_ONCE(attn_fwd_f16_kernel, smem);
   attn_fwd_f16_kernel<<<persistent_grid(p.total_items), kThreads, smem, stream>>>(tmQKV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_f16_kernel");
@@ -840,7 +862,7 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale;
-  constexpr int smem = 2 * kTile128 + 4 * kTile64 + kBoxBytes + 256 + 1024;
+  constexpr int smem = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + 1024;
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem);
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem);
   const int grid = persistent_grid(p.total_items);

@@ -1,5 +1,5 @@
 """Tiny launch scripts for `ncu --set full` captures (one kernel family per invocation):
-    python tests/ncu_target.py gemm|gemm2|attn|vq|ln"""
+    python tests/ncu_target.py gemm|gemm2|gemm16|attn|attn16|vq|ln"""
 import sys
 
 import torch
@@ -25,6 +25,24 @@ elif what == "attn":
     do = ops.round_tf32(torch.randn(B * N, heads * dh, device="cuda"))
     for _ in range(2):
         ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125, True)
+elif what == "attn16":
+    B, N, heads, dh = 32, 1024, 12, 64
+    qkv = torch.randn(B * N, 3 * heads * dh, device="cuda").half()
+    for _ in range(2):
+        o, lse = ops.attention_f16_fwd(qkv, B, N, heads, dh, 0.125)
+    do = torch.randn(B * N, heads * dh, device="cuda").half()
+    for _ in range(2):
+        ops.attention_f16_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125)
+elif what == "gemm16":
+    M, N, K = 131072, 2304, 768
+    a = torch.randn(M, K, device="cuda").half(); b = torch.randn(N, K, device="cuda").half()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    for _ in range(3):
+        ops.gemm(a, b, M, N, K, out=out, cta_group=2, out_half=True)
+    a2 = torch.randn(M, 3072, device="cuda").half(); b2 = torch.randn(768, 3072, device="cuda").half()
+    out2 = torch.empty(M, 768, device="cuda")
+    for _ in range(3):
+        ops.gemm(a2, b2, M, 768, 3072, out=out2, cta_group=2)
 elif what == "vq":
     z = torch.randn(131072, 32, device="cuda"); E = torch.randn(8192, 32, device="cuda")
     for _ in range(3):
