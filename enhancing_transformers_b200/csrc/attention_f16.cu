@@ -33,7 +33,7 @@ constexpr int kBoxBytes = kSoftmaxWarps * 2048;   // one 32-row x 64-byte store 
 // Shared-memory rings.  The loop-carried tiles are small in fp16 (16 KB per 128 rows), so the rings are deep enough to
 // cover a full TMA round trip (~1500 cycles from "stage free" to "bytes landed"): with the 2-deep rings inherited from
 // the tf32 kernels every sub-tile waited for its own load (ncu: the softmax warps' top stall is the wait for S).
-constexpr int kFwdStages = 3;      // K and V rings of the forward kernel (128-row tiles)
+constexpr int kFwdStages = 4;      // K and V rings of the forward kernel (128-row tiles)
 constexpr int kBwdStages = 4;      // [Q64 | dO64] / [K64 | V64] rings of the backward kernels
 
 // named barrier of the four softmax warps that share TMEM lane quarter q (ids 2..5, 128 threads)
@@ -134,9 +134,8 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint8_t* Qs = smem;                              // [2]: the next item's Q tile loads while this item computes
   uint8_t* Ks = smem + 2 * kTile128;               // [NST]
   uint8_t* Vs = smem + (2 + NST) * kTile128;       // [NST]
-  uint8_t* obox = smem + (2 + 2 * NST) * kTile128;                    // 8 store boxes of 32 rows x 64 B (group 0 stores)
-  float* oxch = reinterpret_cast<float*>(obox + kBoxBytes);           // [8 warps][32][32] partial outputs of group 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes + 8 * 32 * 32 * 4);
+  uint8_t* obox = smem + (2 + 2 * NST) * kTile128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
   uint64_t* q_full = bars + 0;    // [2]
   uint64_t* q_empty = bars + 2;   // [2]
   uint64_t* s_full = bars + 4;    // [2]
@@ -149,7 +148,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* v_full = k_full + 2 * NST;      // [NST]
   uint64_t* v_empty = k_full + 3 * NST;     // [NST]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_full + 4 * NST);
-  float* xch = reinterpret_cast<float*>(k_full + 4 * NST + 2);   // [2 groups][2][128] row-max exchange, then [4][128] m and [4][128] l for the merge
+  float* xch = reinterpret_cast<float*>(k_full + 4 * NST + 2);   // [2][4][128] row-max (double buffered) + [4][128] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -160,8 +159,8 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);          // buffer s belongs to softmax group s (8 warps)
-      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 8);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], kSoftmaxWarps);
       mbar_init(&sfree[s], 1);
     }
     fence_barrier_init();
@@ -260,29 +259,17 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
     }
   } else {
-    // ---- softmax / output warps: TWO groups of eight warps on alternate key tiles.
-    // The per-tile softmax is a chain of latencies (TMEM load, row-max exchange, ex2, TMEM store, mbarrier round
-    // trips: ~2000 cycles whatever the per-thread work -- measured: 8 vs 16 warps on ONE tile at a time ran at the
-    // same speed), so group g owns S / P buffer g and every tile of global parity g, with its own running
-    // (max, sum, output) -- while one group sits in a latency, the other one computes.  At the end of an item the
-    // partial results are merged flash-decoding style: o = o0 2^((m0-m)c) + o1 2^((m1-m)c), same for the row sums.
-    // Inside a group a query row (TMEM lane) is shared by two threads: each owns 64 of the tile's 128 scores and 32
-    // of the 64 output columns (row max exchanged per tile under a 64-thread named barrier).
+    // ---- softmax / output warps: a query row (TMEM lane) is shared by four threads (warps of the same lane quarter),
+    // each owning 32 of the tile's 128 scores and 16 of the 64 output columns; the row max (per tile) and the row sum
+    // (once per item) are exchanged through shared memory under a 128-thread named barrier.
     const int q = warp & 3;
-    const int half = ((warp - 2) >> 2) & 1;
-    const int grp = (warp - 2) >> 3;
-    constexpr int OC = DH / 2;
+    const int sub = (warp - 2) >> 2;
+    constexpr int OC = DH / 4;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const float c = p.scale * kLog2eF;
-    float* xs = xch + grp * 256;                 // [2 halves][128 rows] row-max exchange of this group
-    float* ms = xch + 512;                       // [2 groups][2 halves][128]: (m, l) of every thread for the merge
-    float* ls = xch + 1024;
-    float* ox = oxch + (size_t)(((warp - 2) & 7) * OC) * 32 + lane;   // group 1 -> group 0 partial outputs, [warp][i][lane]
-    const auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + grp * 4 + q) : "memory"); };
-    const auto quad_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(10 + q) : "memory"); };
-    uint32_t t0 = 0;                             // global index of the item's first key tile
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, t0 += T) {
+    uint32_t t_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -290,98 +277,79 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
       for (int i = 0; i < OC; ++i) o[i] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-      auto fold_pv = [&](uint32_t t, float alpha) {      // o = o * alpha + P_t V_t (its barrier has been waited on)
+      auto fold_pv = [&](uint32_t it, float alpha) {
+        const int sp = it & 1;
         uint32_t v[OC];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + grp * 64 + half * OC, v);
+        tmem_ld_32x16(tmem_base + lane_off + 256 + sp * 64 + sub * OC, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[grp]);
+        if (lane == 0) mbar_arrive(&o_empty[sp]);
       };
-      const uint32_t first = t0 + ((grp - t0) & 1u);
-      for (uint32_t t = first; t < t0 + T; t += 2) {
-        const int j = (int)(t - t0);
-        if (t != first) {                                 // fold the previous tile of this group before touching the new one:
-          mbar_wait(&o_full[grp], ((t - 2) >> 1) & 1);    // its P.V finished long ago, and issuer B needs the accumulator back
-          tcgen05_fence_after();
-          fold_pv(t - 2, alpha_prev);
-        }
-        mbar_wait(&s_full[grp], (t >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v0[32], v1[32];
-        {
-          const uint32_t s0 = tmem_base + lane_off + grp * 128 + half * 64;
-          tmem_ld_32x32(s0, v0);
-          tmem_ld_32x32(s0 + 32, v1);
-        }
-        tmem_ld_wait();
-        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
-        if (kv_left < 64) {
+      uint32_t v0[32];
+      mbar_wait(&s_full[t_it & 1], (t_it >> 1) & 1);
+      tcgen05_fence_after();
+      tmem_ld_32x32(tmem_base + lane_off + (t_it & 1) * 128 + sub * 32, v0);
+      tmem_ld_wait();
+      for (int j = 0; j < T; ++j, ++t_it) {
+        const int s = t_it & 1;
+        const int kv_left = p.N - j * 128 - sub * 32;       // this thread's columns >= kv_left are padding
+        if (kv_left < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_left) v0[i] = 0xff800000u;        // -inf
-            if (32 + i >= kv_left) v1[i] = 0xff800000u;
-          }
+          for (int i = 0; i < 32; ++i)
+            if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
         }
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        xs[half * 128 + row_in_tile] = mx;
-        pair_bar();        // also orders the partner's S loads before this thread's packed P stores (they overlap its columns)
-        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row_in_tile]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v0[i]));
+        float* xs = xch + (t_it & 1) * 512;
+        xs[sub * 128 + row_in_tile] = mx;
+        quad_bar(q);        // also orders the partners' S loads before this thread's packed P stores (they overlap their columns)
+        mx = fmaxf(fmaxf(xs[row_in_tile], xs[128 + row_in_tile]), fmaxf(xs[256 + row_in_tile], xs[384 + row_in_tile]));
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
         float sum = 0.f, sum1 = 0.f;
-        uint32_t pk[32];       // this thread's 64 probabilities as 32 packed fp16 pairs
+        uint32_t pk[16];       // this thread's 32 probabilities as 16 packed fp16 pairs (keys sub*32 + 2i, +1)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a0 = ex2_approx(fmaf(__uint_as_float(v0[2 * i]), c, -mc));
           const float a1 = ex2_approx(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc));
-          const float b0 = ex2_approx(fmaf(__uint_as_float(v1[2 * i]), c, -mc));
-          const float b1 = ex2_approx(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc));
-          sum += a0 + a1; sum1 += b0 + b1;
+          sum += a0; sum1 += a1;
           pk[i] = pack_h2(a0, a1);
-          pk[16 + i] = pack_h2(b0, b1);
         }
-        pair_bar();            // the partner has read xs: the next tile of this group may overwrite it
-        tmem_st_32x32(tmem_base + lane_off + grp * 128 + half * 32, pk);     // P columns [0,64) of the S buffer
+        sum += sum1;
+        tmem_st_32x16(tmem_base + lane_off + s * 128 + sub * 16, pk);     // P columns [0,64) of the S buffer
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[grp]);
-        l = fmaf(l, alpha, sum + sum1);
+        if (lane == 0) mbar_arrive(&p_full[s]);
+        l = fmaf(l, alpha, sum);
+        const bool more = j + 1 < T;
+        const uint32_t ph_s = ((t_it + 1) >> 1) & 1, ph_o = ((t_it - 1) >> 1) & 1;
+        if (more && j >= 1) mbar_wait2(&s_full[s ^ 1], ph_s, &o_full[s ^ 1], ph_o);
+        else if (more)      mbar_wait(&s_full[s ^ 1], ph_s);
+        else if (j >= 1)    mbar_wait(&o_full[s ^ 1], ph_o);
+        tcgen05_fence_after();
+        if (more) tmem_ld_32x32(tmem_base + lane_off + (s ^ 1) * 128 + sub * 32, v0);
+        if (j >= 1) fold_pv(t_it - 1, alpha_prev);
+        else        tmem_ld_wait();
         alpha_prev = alpha;
         m = m_new;
       }
-      if (first < t0 + T) {                               // this group's last tile of the item
-        const uint32_t last = first + ((t0 + T - 1 - first) & ~1u);
-        mbar_wait(&o_full[grp], (last >> 1) & 1);
-        tcgen05_fence_after();
-        fold_pv(last, alpha_prev);
-      }
-      // ---- merge the two groups (group 1 hands its partial row over through shared memory)
-      ms[(grp * 2 + half) * 128 + row_in_tile] = m;
-      ls[(grp * 2 + half) * 128 + row_in_tile] = l;
-      if (grp == 1) {
-#pragma unroll
-        for (int i = 0; i < OC; ++i) ox[i * 32] = o[i];
-      }
-      quad_bar();
-      if (grp == 0) {
-        const float m1 = ms[(2 + half) * 128 + row_in_tile];
-        const float mm = fmaxf(m, m1);                    // finite: every item has at least one tile
-        const float a0 = ex2_approx((m - mm) * c), a1 = ex2_approx((m1 - mm) * c);
-        const float lt = (ls[row_in_tile] + ls[128 + row_in_tile]) * a0 + (ls[256 + row_in_tile] + ls[384 + row_in_tile]) * a1;
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = o[i] * a0 + ox[i * 32] * a1;
-        const int row = qt * 128 + row_in_tile;
-        store_box_h(obox + (warp - 2) * 4096, &tmO, o, 1.f / lt, h * DH + half * OC, qt * 128 + q * 32, b, lane);
-        if (row < p.N && half == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = mm * p.scale + logf(lt);
-      }
-      quad_bar();              // the exchange buffers are rewritten by the next item only after group 0 has read them
+      mbar_wait(&o_full[(t_it - 1) & 1], ((t_it - 1) >> 1) & 1);
+      tcgen05_fence_after();
+      fold_pv(t_it - 1, alpha_prev);
+      float* ls = xch + 1024;
+      ls[sub * 128 + row_in_tile] = l;
+      quad_bar(q);
+      l = (ls[row_in_tile] + ls[128 + row_in_tile]) + (ls[256 + row_in_tile] + ls[384 + row_in_tile]);
+      const int row = qt * 128 + row_in_tile;
+      store_box_h16(obox + (warp - 2) * 2048, &tmO, o, 1.f / l, h * DH + sub * OC, qt * 128 + q * 32, b, lane);
+      if (row < p.N && sub == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m * p.scale + logf(l);
+      quad_bar(q);     // ls is rewritten by the next item only after every partner has read it
     }
     if (lane == 0) bulk_wait_group_read<0>();
   }
@@ -400,9 +368,11 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 //   dQ : item = (batch, head, 128-query tile), loop over 64-key sub-tiles:
 //        S = Q K^T, dP = dO V^T; dS packed; dQ += dS K
 // A 64-row fp16 tile is used both K-major (score MMAs) and MN-major (gradient MMAs) from one shared-memory image.
-// Packed operands: thread `sub` (0..3) of a row owns 16 of the 64 columns of a sub-tile and writes its 8 packed columns
-// at the start of its own 16-column range, so no thread overwrites scores another one has not loaded yet:
-// A-operand k-step k (16 contraction indices = thread k's columns) lives at column k * 16 of the buffer.
+// Softmax warps: two groups of eight on alternate sub-tiles (group g owns TMEM buffer g; the per-sub-tile work is a
+// chain of TMEM / mbarrier latencies, so two chains in flight double the rate).  Inside a group a row is shared by two
+// threads; thread `half` owns 32 of the 64 columns of a sub-tile and writes its 16 packed columns at the start of its
+// own 32-column range, so no thread overwrites scores the other one has not loaded yet:
+// A-operand k-step k (16 contraction indices) lives at column (k >> 1) * 32 + (k & 1) * 8 of the buffer.
 // =============================================================================================
 struct BwdParams {
   const float* lse;
@@ -411,7 +381,7 @@ struct BwdParams {
   float scale;
 };
 
-__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)(k * 16); }
+__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)((k >> 1) * 32 + (k & 1) * 8); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
@@ -440,7 +410,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     for (int s = 0; s < NST; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);           // buffer s belongs to softmax group s (8 warps)
       mbar_init(&sfree[s], 1);
     }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
@@ -547,44 +517,45 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
     }
   } else {
-    // 16 softmax warps: the four warps of a TMEM lane quarter (key rows) split the 64 query columns of a sub-tile;
-    // at the end of an item warps sub 0,1 store dV (32 columns each), warps sub 2,3 store dK.
+    // softmax warps (two groups, see above): thread = key row; at the end of an item warps sub 0,1 store dV
+    // (32 columns each), warps sub 2,3 store dK.
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
+    const int half = sub & 1, grp = sub >> 1;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+    uint32_t t0 = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it, t0 += NS) {
       const int kt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // per-column lse / delta: lane l keeps the values of query column sub*16 + (l & 15) of the current sub-tile in
-      // registers (fetched one sub-tile ahead) and the 16 columns are broadcast with warp shuffles (see attention_tc.cu)
-      const int qcol = sub * 16 + (lane & 15);
+      // per-column lse / delta: lane l keeps the values of query column half*32 + l of the group's current sub-tile in
+      // registers (fetched one of its sub-tiles ahead) and the 32 columns are broadcast with warp shuffles
+      const uint32_t first = t0 + ((grp - t0) & 1u);
+      const int qcol = half * 32 + lane;
       float raw_l = 0.f, raw_e = 0.f;
-      bool nvalid = qcol < p.N;
-      if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
-      for (int i = 0; i < NS; ++i, ++t_it) {
-        const int s = t_it & 1;
+      bool nvalid = first < t0 + NS && (int)(first - t0) * 64 + qcol < p.N;
+      if (nvalid) { raw_l = lb[(first - t0) * 64 + qcol]; raw_e = eb[(first - t0) * 64 + qcol]; }
+      for (uint32_t t = first; t < t0 + NS; t += 2) {
         const float myL = nvalid ? raw_l * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
         const float myE = nvalid ? raw_e : 0.f;
         {
-          const int qi = (i + 1) * 64 + qcol;
-          nvalid = i + 1 < NS && qi < p.N;
+          const int qi = (int)(t + 2 - t0) * 64 + qcol;
+          nvalid = t + 2 < t0 + NS && qi < p.N;
           if (nvalid) { raw_l = lb[qi]; raw_e = eb[qi]; }
         }
-        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+        mbar_wait(&s_full[grp], (t >> 1) & 1);
         tcgen05_fence_after();
-        const int col = s * 64 + sub * 16;
-        uint32_t v[16], g[16];
-        tmem_ld_32x16(tmem_base + lane_off + col, v);
-        tmem_ld_32x16(tmem_base + lane_off + 128 + col, g);
+        const int col = grp * 64 + half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        uint32_t pp[8], ds[8];
+        uint32_t pp[16], ds[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float L0 = __shfl_sync(0xffffffffu, myL, 2 * j), L1 = __shfl_sync(0xffffffffu, myL, 2 * j + 1);
           const float E0 = __shfl_sync(0xffffffffu, myE, 2 * j), E1 = __shfl_sync(0xffffffffu, myE, 2 * j + 1);
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
@@ -592,12 +563,12 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           pp[j] = pack_h2(p0, p1);
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - E0), p1 * (__uint_as_float(g[2 * j + 1]) - E1));
         }
-        tmem_st_32x8(tmem_base + lane_off + col, pp);
-        tmem_st_32x8(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x16(tmem_base + lane_off + col, pp);
+        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
+        if (lane == 0) mbar_arrive(&p_full[grp]);
       }
       // item epilogue: dV lives in TMEM columns [256,320), dK in [320,384): warp `sub` takes columns 256 + sub*32
       mbar_wait(acc_full, item_it & 1);
@@ -653,7 +624,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     for (int s = 0; s < NST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
       mbar_init(&sfree[s], 1);
     }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
@@ -756,15 +727,16 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       }
     }
   } else {
-    // 16 softmax warps: thread = query row, the four warps of a lane quarter split the 64 key columns of a sub-tile
-    // and, at the end of an item, the 64 columns of dQ
+    // softmax warps (two groups on alternate sub-tiles): thread = query row, a row shared by the two threads of a group;
+    // at the end of an item all sixteen warps store 16 columns of dQ each
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
+    const int half = sub & 1, grp = sub >> 1;
     constexpr int OC = DH / 4;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
-    uint32_t t_it = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+    uint32_t t0 = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it, t0 += NS) {
       const int qt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -772,30 +744,29 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const long long sidx = ((long long)b * p.heads + h) * p.N + row;
       const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
-      for (int i = 0; i < NS; ++i, ++t_it) {
-        const int s = t_it & 1;
-        mbar_wait(&s_full[s], (t_it >> 1) & 1);
+      for (uint32_t t = t0 + ((grp - t0) & 1u); t < t0 + NS; t += 2) {
+        mbar_wait(&s_full[grp], (t >> 1) & 1);
         tcgen05_fence_after();
-        const int col = s * 64 + sub * 16;
-        const int kv_left = p.N - i * 64 - sub * 16;
-        uint32_t v[16], g[16];
-        tmem_ld_32x16(tmem_base + lane_off + col, v);
-        tmem_ld_32x16(tmem_base + lane_off + 128 + col, g);
+        const int col = grp * 64 + half * 32;
+        const int kv_left = p.N - (int)(t - t0) * 64 - half * 32;
+        uint32_t v[32], g[32];
+        tmem_ld_32x32(tmem_base + lane_off + col, v);
+        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
-        uint32_t ds[8];
+        uint32_t ds[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
           float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
           if (2 * j >= kv_left) p0 = 0.f;            // ragged last tile: padded key columns contribute nothing
           if (2 * j + 1 >= kv_left) p1 = 0.f;
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
         }
-        tmem_st_32x8(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
+        if (lane == 0) mbar_arrive(&p_full[grp]);
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -855,13 +826,13 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   CUtensorMap tmQKV, tmO;
   int rc;
   if ((rc = make_tile_map(&tmQKV, qkv, 3ll * inner, N, B, 128))) return rc;
-  if ((rc = make_store_map(&tmO, out, inner, N, B, 32))) return rc;
+  if ((rc = make_store_map(&tmO, out, inner, N, B, 16))) return rc;
   FwdParams p;
   p.lse = lse; p.N = N; p.heads = heads;
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
   p.scale = scale;
-  constexpr int smem = (2 + 2 * kFwdStages) * kTile128 + kBoxBytes + 8 * 32 * 32 * 4 + 512 + 1536 * 4 + 1024;
+  constexpr int smem = (2 + 2 * kFwdStages) * kTile128 + kBoxBytes + 512 + 1536 * 4 + 1024;
   B200_CONFIGURE_SMEM_ONCE(attn_fwd_f16_kernel, smem);
   attn_fwd_f16_kernel<<<persistent_grid(p.total_items), kThreads, smem, stream>>>(tmQKV, tmO, p);
   B200_LAUNCH_OK("attn_fwd_f16_kernel");
