@@ -368,11 +368,9 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 //   dQ : item = (batch, head, 128-query tile), loop over 64-key sub-tiles:
 //        S = Q K^T, dP = dO V^T; dS packed; dQ += dS K
 // A 64-row fp16 tile is used both K-major (score MMAs) and MN-major (gradient MMAs) from one shared-memory image.
-// Softmax warps: two groups of eight on alternate sub-tiles (group g owns TMEM buffer g; the per-sub-tile work is a
-// chain of TMEM / mbarrier latencies, so two chains in flight double the rate).  Inside a group a row is shared by two
-// threads; thread `half` owns 32 of the 64 columns of a sub-tile and writes its 16 packed columns at the start of its
-// own 32-column range, so no thread overwrites scores the other one has not loaded yet:
-// A-operand k-step k (16 contraction indices) lives at column (k >> 1) * 32 + (k & 1) * 8 of the buffer.
+// Packed operands: thread `sub` (0..3) of a row owns 16 of the 64 columns of a sub-tile and writes its 8 packed columns
+// at the start of its own 16-column range, so no thread overwrites scores another one has not loaded yet:
+// A-operand k-step k (16 contraction indices = thread k's columns) lives at column k * 16 of the buffer.
 // =============================================================================================
 struct BwdParams {
   const float* lse;
@@ -381,7 +379,13 @@ struct BwdParams {
   float scale;
 };
 
-__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)((k >> 1) * 32 + (k & 1) * 8); }
+__device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)(k * 16); }
+// TMEM plan of both backward kernels: THREE score buffers (the loop is a chain S-MMA -> softmax -> gradient MMA -> S-MMA of
+// the same buffer, dominated by commit / mbarrier / tcgen05.ld-st latencies: its rate is buffers / round-trip time).
+//   S or S^T buffers at columns [0,64) [64,128) [128,192); dP or dP^T buffers at [192,256) [256,320) [320,384);
+//   accumulators at [384,448) (dV or dQ) and [448,512) (dK)
+constexpr int kTB = 3;
+constexpr uint32_t kColDP = 192, kColAcc = 384;
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
@@ -395,12 +399,12 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
   uint64_t* kv_full = bars + 0;    // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
-  uint64_t* s_full = bars + 4;     // [2]
-  uint64_t* p_full = bars + 6;     // [2]
-  uint64_t* acc_full = bars + 8;
-  uint64_t* acc_empty = bars + 9;
-  uint64_t* sfree = bars + 10;     // [2]
-  uint64_t* qd_full = bars + 12;          // [NST]
+  uint64_t* acc_full = bars + 4;
+  uint64_t* acc_empty = bars + 5;
+  uint64_t* s_full = bars + 6;     // [kTB]
+  uint64_t* p_full = bars + 9;     // [kTB]
+  uint64_t* sfree = bars + 12;     // [kTB]
+  uint64_t* qd_full = bars + 15;          // [NST]
   uint64_t* qd_empty = qd_full + NST;     // [NST] two arrivals: the score MMAs and the gradient MMAs have both read the stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qd_full + 2 * NST);
 
@@ -408,11 +412,8 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
     for (int s = 0; s < NST; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);           // buffer s belongs to softmax group s (8 warps)
-      mbar_init(&sfree[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps); mbar_init(&sfree[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
@@ -463,8 +464,8 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const uint64_t kd = desc_advance(kd0, ib * 2 * kTile128);
       const uint64_t vd = desc_advance(kd, kTile128);
       for (int i = 0; i < NS; ++i, ++sd_it) {
-        const int s = sd_it & 1;                      // TMEM S^T / dP^T buffer
-        const uint32_t ph = (sd_it >> 1) & 1;
+        const int s = sd_it % kTB;                    // TMEM S^T / dP^T buffer
+        const uint32_t ph = (sd_it / kTB) & 1;
         const int r = sd_it % NST;                    // ring stage
         mbar_wait(&qd_full[r], (sd_it / NST) & 1);
         mbar_wait(&sfree[s], ph ^ 1);
@@ -477,7 +478,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
             umma_f16<1>(tmem_base + s * 64, desc_advance(kd, k * kKStepK), desc_advance(qd, k * kKStepK), idesc_s, k != 0);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
-            umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(vd, k * kKStepK), desc_advance(dd, k * kKStepK), idesc_s, k != 0);
+            umma_f16<1>(tmem_base + kColDP + s * 64, desc_advance(vd, k * kKStepK), desc_advance(dd, k * kKStepK), idesc_s, k != 0);
           umma_commit<1>(&s_full[s]);
           umma_commit<1>(&qd_empty[r]);
           if (i == NS - 1) umma_commit<1>(&kv_empty[ib]);
@@ -492,8 +493,8 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     uint32_t dv_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       for (int i = 0; i < NS; ++i, ++dv_it) {
-        const int s = dv_it & 1;
-        const uint32_t ph = (dv_it >> 1) & 1;
+        const int s = dv_it % kTB;
+        const uint32_t ph = (dv_it / kTB) & 1;
         const int r = dv_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
         mbar_wait(&qd_full[r], (dv_it / NST) & 1);
@@ -505,10 +506,10 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           const uint32_t acc_on = i > 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // dV += P^T dO      (64 queries = 4 x UMMA_K)
-            umma_f16_ts(tmem_base + 256, tmem_base + s * 64 + packed_a_col(k), desc_advance(dmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+            umma_f16_ts(tmem_base + kColAcc, tmem_base + s * 64 + packed_a_col(k), desc_advance(dmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // dK += dS^T Q
-            umma_f16_ts(tmem_base + 320, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(qmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+            umma_f16_ts(tmem_base + kColAcc + 64, tmem_base + kColDP + s * 64 + packed_a_col(k), desc_advance(qmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
           umma_commit<1>(&qd_empty[r]);
           umma_commit<1>(&sfree[s]);
           if (i == NS - 1) umma_commit<1>(acc_full);
@@ -517,45 +518,44 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
     }
   } else {
-    // softmax warps (two groups, see above): thread = key row; at the end of an item warps sub 0,1 store dV
-    // (32 columns each), warps sub 2,3 store dK.
+    // 16 softmax warps: the four warps of a TMEM lane quarter (key rows) split the 64 query columns of a sub-tile;
+    // at the end of an item warps sub 0,1 store dV (32 columns each), warps sub 2,3 store dK.
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
-    const int half = sub & 1, grp = sub >> 1;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
-    uint32_t t0 = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it, t0 += NS) {
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       const int kt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // per-column lse / delta: lane l keeps the values of query column half*32 + l of the group's current sub-tile in
-      // registers (fetched one of its sub-tiles ahead) and the 32 columns are broadcast with warp shuffles
-      const uint32_t first = t0 + ((grp - t0) & 1u);
-      const int qcol = half * 32 + lane;
+      // per-column lse / delta: lane l keeps the values of query column sub*16 + (l & 15) of the current sub-tile in
+      // registers (fetched one sub-tile ahead) and the 16 columns are broadcast with warp shuffles (see attention_tc.cu)
+      const int qcol = sub * 16 + (lane & 15);
       float raw_l = 0.f, raw_e = 0.f;
-      bool nvalid = first < t0 + NS && (int)(first - t0) * 64 + qcol < p.N;
-      if (nvalid) { raw_l = lb[(first - t0) * 64 + qcol]; raw_e = eb[(first - t0) * 64 + qcol]; }
-      for (uint32_t t = first; t < t0 + NS; t += 2) {
+      bool nvalid = qcol < p.N;
+      if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it % kTB;
         const float myL = nvalid ? raw_l * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
         const float myE = nvalid ? raw_e : 0.f;
         {
-          const int qi = (int)(t + 2 - t0) * 64 + qcol;
-          nvalid = t + 2 < t0 + NS && qi < p.N;
+          const int qi = (i + 1) * 64 + qcol;
+          nvalid = i + 1 < NS && qi < p.N;
           if (nvalid) { raw_l = lb[qi]; raw_e = eb[qi]; }
         }
-        mbar_wait(&s_full[grp], (t >> 1) & 1);
+        mbar_wait(&s_full[s], (t_it / kTB) & 1);
         tcgen05_fence_after();
-        const int col = grp * 64 + half * 32;
-        uint32_t v[32], g[32];
-        tmem_ld_32x32(tmem_base + lane_off + col, v);
-        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        const int col = s * 64 + sub * 16;
+        uint32_t v[16], g[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, v);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, g);
         tmem_ld_wait();
-        uint32_t pp[16], ds[16];
+        uint32_t pp[8], ds[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float L0 = __shfl_sync(0xffffffffu, myL, 2 * j), L1 = __shfl_sync(0xffffffffu, myL, 2 * j + 1);
           const float E0 = __shfl_sync(0xffffffffu, myE, 2 * j), E1 = __shfl_sync(0xffffffffu, myE, 2 * j + 1);
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
@@ -563,19 +563,19 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           pp[j] = pack_h2(p0, p1);
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - E0), p1 * (__uint_as_float(g[2 * j + 1]) - E1));
         }
-        tmem_st_32x16(tmem_base + lane_off + col, pp);
-        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x8(tmem_base + lane_off + col, pp);
+        tmem_st_32x8(tmem_base + lane_off + kColDP + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[grp]);
+        if (lane == 0) mbar_arrive(&p_full[s]);
       }
-      // item epilogue: dV lives in TMEM columns [256,320), dK in [320,384): warp `sub` takes columns 256 + sub*32
+      // item epilogue: dV lives in TMEM columns [384,448), dK in [448,512): warp `sub` takes columns 384 + sub*32
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
       {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_off + 256 + sub * 32, v);
+        tmem_ld_32x32(tmem_base + lane_off + kColAcc + sub * 32, v);
         tmem_ld_wait();
         float r[32];
 #pragma unroll
@@ -609,12 +609,12 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
   uint64_t* q_full = bars + 0;     // [2]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* s_full = bars + 4;     // [2]
-  uint64_t* p_full = bars + 6;     // [2]
-  uint64_t* acc_full = bars + 8;
-  uint64_t* acc_empty = bars + 9;
-  uint64_t* sfree = bars + 10;     // [2]
-  uint64_t* kv_full = bars + 12;          // [NST]
+  uint64_t* acc_full = bars + 4;
+  uint64_t* acc_empty = bars + 5;
+  uint64_t* s_full = bars + 6;     // [kTB]
+  uint64_t* p_full = bars + 9;     // [kTB]
+  uint64_t* sfree = bars + 12;     // [kTB]
+  uint64_t* kv_full = bars + 15;          // [NST]
   uint64_t* kv_empty = kv_full + NST;     // [NST] two arrivals (score MMAs, dQ MMAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_full + 2 * NST);
 
@@ -622,11 +622,8 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmQKV64);
     for (int s = 0; s < NST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8);
-      mbar_init(&sfree[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps); mbar_init(&sfree[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
@@ -677,8 +674,8 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const uint64_t qd = desc_advance(qd0, ib * 2 * kTile128);
       const uint64_t dd = desc_advance(qd, kTile128);
       for (int i = 0; i < NS; ++i, ++sd_it) {
-        const int s = sd_it & 1;
-        const uint32_t ph = (sd_it >> 1) & 1;
+        const int s = sd_it % kTB;
+        const uint32_t ph = (sd_it / kTB) & 1;
         const int r = sd_it % NST;
         mbar_wait(&kv_full[r], (sd_it / NST) & 1);
         mbar_wait(&sfree[s], ph ^ 1);
@@ -691,7 +688,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
             umma_f16<1>(tmem_base + s * 64, desc_advance(qd, k * kKStepK), desc_advance(kkd, k * kKStepK), idesc_s, k != 0);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
-            umma_f16<1>(tmem_base + 128 + s * 64, desc_advance(dd, k * kKStepK), desc_advance(vkd, k * kKStepK), idesc_s, k != 0);
+            umma_f16<1>(tmem_base + kColDP + s * 64, desc_advance(dd, k * kKStepK), desc_advance(vkd, k * kKStepK), idesc_s, k != 0);
           umma_commit<1>(&s_full[s]);
           umma_commit<1>(&kv_empty[r]);
           if (i == NS - 1) umma_commit<1>(&q_empty[ib]);
@@ -706,8 +703,8 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     uint32_t dq_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       for (int i = 0; i < NS; ++i, ++dq_it) {
-        const int s = dq_it & 1;
-        const uint32_t ph = (dq_it >> 1) & 1;
+        const int s = dq_it % kTB;
+        const uint32_t ph = (dq_it / kTB) & 1;
         const int r = dq_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
         mbar_wait(&kv_full[r], (dq_it / NST) & 1);
@@ -718,7 +715,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           const uint32_t acc_on = i > 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ts(tmem_base + 256, tmem_base + 128 + s * 64 + packed_a_col(k), desc_advance(kmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
+            umma_f16_ts(tmem_base + kColAcc, tmem_base + kColDP + s * 64 + packed_a_col(k), desc_advance(kmd, k * kKStepMN), idesc_g, acc_on | (k != 0));
           umma_commit<1>(&kv_empty[r]);
           umma_commit<1>(&sfree[s]);
           if (i == NS - 1) umma_commit<1>(acc_full);
@@ -727,16 +724,15 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       }
     }
   } else {
-    // softmax warps (two groups on alternate sub-tiles): thread = query row, a row shared by the two threads of a group;
-    // at the end of an item all sixteen warps store 16 columns of dQ each
+    // 16 softmax warps: thread = query row, the four warps of a lane quarter split the 64 key columns of a sub-tile
+    // and, at the end of an item, the 64 columns of dQ
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
-    const int half = sub & 1, grp = sub >> 1;
     constexpr int OC = DH / 4;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
-    uint32_t t0 = 0, item_it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it, t0 += NS) {
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       const int qt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -744,35 +740,36 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const long long sidx = ((long long)b * p.heads + h) * p.N + row;
       const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
       const float dl = row < p.N ? p.delta[sidx] : 0.f;
-      for (uint32_t t = t0 + ((grp - t0) & 1u); t < t0 + NS; t += 2) {
-        mbar_wait(&s_full[grp], (t >> 1) & 1);
+      for (int i = 0; i < NS; ++i, ++t_it) {
+        const int s = t_it % kTB;
+        mbar_wait(&s_full[s], (t_it / kTB) & 1);
         tcgen05_fence_after();
-        const int col = grp * 64 + half * 32;
-        const int kv_left = p.N - (int)(t - t0) * 64 - half * 32;
-        uint32_t v[32], g[32];
-        tmem_ld_32x32(tmem_base + lane_off + col, v);
-        tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
+        const int col = s * 64 + sub * 16;
+        const int kv_left = p.N - i * 64 - sub * 16;
+        uint32_t v[16], g[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, v);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, g);
         tmem_ld_wait();
-        uint32_t ds[16];
+        uint32_t ds[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
           float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
           if (2 * j >= kv_left) p0 = 0.f;            // ragged last tile: padded key columns contribute nothing
           if (2 * j + 1 >= kv_left) p1 = 0.f;
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
         }
-        tmem_st_32x16(tmem_base + lane_off + 128 + col, ds);
+        tmem_st_32x8(tmem_base + lane_off + kColDP + col, ds);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[grp]);
+        if (lane == 0) mbar_arrive(&p_full[s]);
       }
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
       {
         uint32_t v[OC];
-        tmem_ld_32x16(tmem_base + lane_off + 256 + sub * OC, v);
+        tmem_ld_32x16(tmem_base + lane_off + kColAcc + sub * OC, v);
         tmem_ld_wait();
         float r[OC];
 #pragma unroll
