@@ -81,8 +81,8 @@ int vq_forward(const float*, const float*, float*, long long*, float*, int, int,
 int vq_backward(const float*, const float*, const long long*, const float*, const float*, float*, float*, int, int, int, int,
                 int, float, int, cudaStream_t);
 int vq_embed(const float*, const long long*, float*, int, int, int, int, int, cudaStream_t);
-int patchify(const float*, float*, int, int, int, int, int, int, cudaStream_t);
-int unpatchify(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int patchify(const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int unpatchify(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 size_t colsum_workspace_bytes(int);
 int colsum(const float*, long long, int, int, float*, void*, size_t, cudaStream_t);
 int round_tf32_copy(const float*, float*, long long, cudaStream_t);
@@ -182,11 +182,11 @@ int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, i
                     void* stream) {
   return vq_embed(E, codes, out, M, K, D, depth, use_norm, S(stream));
 }
-int b200vq_patchify(const float* img, float* patches, int B, int C, int H, int W, int p, int round_out, void* stream) {
-  return patchify(img, patches, B, C, H, W, p, round_out, S(stream));
+int b200vq_patchify(const float* img, float* patches, int B, int C, int H, int W, int ph, int pw, int round_out, void* stream) {
+  return patchify(img, patches, B, C, H, W, ph, pw, round_out, S(stream));
 }
-int b200vq_unpatchify(const float* tokens, const float* bias, float* img, int B, int C, int H, int W, int p, void* stream) {
-  return unpatchify(tokens, bias, img, B, C, H, W, p, S(stream));
+int b200vq_unpatchify(const float* tokens, const float* bias, float* img, int B, int C, int H, int W, int ph, int pw, void* stream) {
+  return unpatchify(tokens, bias, img, B, C, H, W, ph, pw, S(stream));
 }
 size_t b200vq_colsum_workspace_bytes(int N) { return colsum_workspace_bytes(N); }
 int b200vq_colsum(const float* X, long long ld, int M, int N, float* out, void* workspace, size_t ws_bytes, void* stream) {

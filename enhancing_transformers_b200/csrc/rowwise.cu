@@ -336,13 +336,13 @@ __global__ void add_rows_mod_kernel(const float* __restrict__ x, const float* __
   }
 }
 
-// img [B,C,H,W] -> patches [B*gh*gw, C*p*p] with the patch vector ordered (c, ph, pw): the
-// im2col of Conv2d(kernel=stride=p) followed by 'b c h w -> b (h w) c' (layers.py:168-171).
-// p % 4 == 0 so that one float4 stays inside a patch row.
-__global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int H, int W, int p,
+// img [B,C,H,W] -> patches [B*gh*gw, C*ph*pw] with the patch vector ordered (c, row, col): the
+// im2col of Conv2d(kernel=stride=(ph,pw)) followed by 'b c h w -> b (h w) c' (layers.py:157-171).
+// pw % 4 == 0 so that one float4 stays inside a patch row.
+__global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int H, int W, int ph_, int pw_,
                                 int round_out) {
-  const int gh = H / p, gw = W / p;
-  const int pd = C * p * p;
+  const int gh = H / ph_, gw = W / pw_;
+  const int pd = C * ph_ * pw_;
   const long long total4 = (long long)B * gh * gw * pd / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     // iterate in *image* order so that global reads are fully coalesced; writes are 16-byte pieces
@@ -354,9 +354,9 @@ __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict
     const int b = (int)(r / C);
     float4 v = reinterpret_cast<const float4*>(img)[i];
     if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-    const int hp = h / p, ph = h % p, wp = w / p, pw = w % p;
+    const int hp = h / ph_, ph = h % ph_, wp = w / pw_, pw = w % pw_;
     const long long row = ((long long)b * gh + hp) * gw + wp;
-    *reinterpret_cast<float4*>(out + row * pd + (c * p + ph) * p + pw) = v;
+    *reinterpret_cast<float4*>(out + row * pd + (c * ph_ + ph) * pw_ + pw) = v;
   }
 }
 
@@ -364,9 +364,9 @@ __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict
 // ConvTranspose2d(kernel=stride=p) after 'b (h w) c -> b c h w' (layers.py:202-205).
 // With bias == nullptr and the roles swapped it is also the backward of patchify.
 __global__ void unpatchify_kernel(const float* __restrict__ tok, const float* __restrict__ bias, float* __restrict__ img,
-                                  int B, int C, int H, int W, int p) {
-  const int gh = H / p, gw = W / p;
-  const int pd = C * p * p;
+                                  int B, int C, int H, int W, int ph_, int pw_) {
+  const int gh = H / ph_, gw = W / pw_;
+  const int pd = C * ph_ * pw_;
   const long long total4 = (long long)B * C * H * W / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
@@ -375,9 +375,9 @@ __global__ void unpatchify_kernel(const float* __restrict__ tok, const float* __
     const int h = (int)(r % H); r /= H;
     const int c = (int)(r % C);
     const int b = (int)(r / C);
-    const int hp = h / p, ph = h % p, wp = w / p, pw = w % p;
+    const int hp = h / ph_, ph = h % ph_, wp = w / pw_, pw = w % pw_;
     const long long row = ((long long)b * gh + hp) * gw + wp;
-    float4 v = *reinterpret_cast<const float4*>(tok + row * pd + (c * p + ph) * p + pw);
+    float4 v = *reinterpret_cast<const float4*>(tok + row * pd + (c * ph_ + ph) * pw_ + pw);
     if (bias) { const float bb = __ldg(bias + c); v.x += bb; v.y += bb; v.z += bb; v.w += bb; }
     reinterpret_cast<float4*>(img)[i] = v;
   }
@@ -532,16 +532,18 @@ int add_rows_mod(const float* x, const float* table, float* out, long long M, in
   return 0;
 }
 
-int patchify(const float* img, float* out, int B, int C, int H, int W, int p, int round_out, cudaStream_t stream) {
-  B200_CHECK_ARG(p % 4 == 0 && H % p == 0 && W % p == 0, "patchify: patch must be a multiple of 4 and divide the image");
-  patchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(img, out, B, C, H, W, p, round_out);
+int patchify(const float* img, float* out, int B, int C, int H, int W, int ph, int pw, int round_out, cudaStream_t stream) {
+  B200_CHECK_ARG(ph > 0 && pw > 0 && pw % 4 == 0 && H % ph == 0 && W % pw == 0,
+                 "patchify: the patch must divide the image and its width must be a multiple of 4 (got %d x %d)", ph, pw);
+  patchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(img, out, B, C, H, W, ph, pw, round_out);
   B200_LAUNCH_OK("patchify_kernel");
   return 0;
 }
 
-int unpatchify(const float* tok, const float* bias, float* img, int B, int C, int H, int W, int p, cudaStream_t stream) {
-  B200_CHECK_ARG(p % 4 == 0 && H % p == 0 && W % p == 0, "unpatchify: patch must be a multiple of 4 and divide the image");
-  unpatchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(tok, bias, img, B, C, H, W, p);
+int unpatchify(const float* tok, const float* bias, float* img, int B, int C, int H, int W, int ph, int pw, cudaStream_t stream) {
+  B200_CHECK_ARG(ph > 0 && pw > 0 && pw % 4 == 0 && H % ph == 0 && W % pw == 0,
+                 "unpatchify: the patch must divide the image and its width must be a multiple of 4 (got %d x %d)", ph, pw);
+  unpatchify_kernel<<<stream_grid((long long)B * C * H * W / 4, 256), 256, 0, stream>>>(tok, bias, img, B, C, H, W, ph, pw);
   B200_LAUNCH_OK("unpatchify_kernel");
   return 0;
 }

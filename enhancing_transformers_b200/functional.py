@@ -468,7 +468,8 @@ class PatchEmbedFn(torch.autograd.Function):
     def forward(ctx, img, w, b, pos, p):
         B, C, H, W = img.shape
         D = w.shape[0]
-        n_tok = (H // p) * (W // p)
+        ph, pw = ops._pair(p)
+        n_tok = (H // ph) * (W // pw)
         mode = "parity" if (PRECISE_IO or _precision == "parity") else "tf32"
         patches = ops.patchify(img, p, mode == "tf32")
         M, pd = patches.shape
@@ -511,7 +512,8 @@ class ToPixelFn(torch.autograd.Function):
     def forward(ctx, x, w, b, B, H, W, p):
         M, D = x.shape
         C = w.shape[1]
-        pd = C * p * p
+        ph, pw = ops._pair(p)
+        pd = C * ph * pw
         mode = "parity" if (PRECISE_IO or _precision == "parity") else "tf32"
         ws = _W(w, mode)
         ws.a = ws.a.view(D, pd)
@@ -529,12 +531,13 @@ class ToPixelFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         B, C, H, W, p, mode = ctx.geom
         M, D = x.shape
-        pd = C * p * p
+        ph, pw = ops._pair(p)
+        pd = C * ph * pw
         # the reference's adaptive GAN weight calls torch.autograd.grad(loss, get_last_layer()) twice per step
         # (vqperceptual.py:97-98): only dw is wanted there, so every product is guarded
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
         dy = ops.patchify(g.contiguous(), p, mode == "tf32")
-        db = ops.colsum(dy).view(C, p * p).sum(dim=1) if need_b else None
+        db = ops.colsum(dy).view(C, ph * pw).sum(dim=1) if need_b else None
         dw = _wgrad(x, dy, D, pd, mode).view_as(w) if need_w else None
         dx = None
         if need_x:

@@ -178,10 +178,13 @@ class _Geometry:
         ih, iw = _pair(image_size)
         ph, pw = _pair(patch_size)
         assert ih % ph == 0 and iw % pw == 0, 'Image dimensions must be divisible by the patch size.'
-        if ph != pw or ph % 4:
-            raise NotImplementedError("b200vq: square patches with side % 4 == 0 only")
+        if pw % 4 or (channels * ph * pw) % 4:
+            # the layout kernels move 16-byte pieces of a patch row and TMA needs 16-byte row strides of the im2col
+            # matrix: a patch width that is not a multiple of 4 has no CUDA path here (every shipped config uses 8)
+            raise NotImplementedError(f"b200vq: patch width must be a multiple of 4 (got {ph} x {pw}); "
+                                      "use the reference modules for this geometry")
         self.image_hw = (ih, iw)
-        self.patch = ph
+        self.patch = (ph, pw)
         self.grid = (ih // ph, iw // pw)
         self.num_patches = self.grid[0] * self.grid[1]
         self.patch_dim = channels * ph * pw

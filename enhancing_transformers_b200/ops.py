@@ -299,18 +299,25 @@ def vq_embed(E: Tensor, codes: Tensor, depth: int, use_norm: bool = True) -> Ten
 
 
 # ---------------------------------------------------------------------------- layout / reductions
-def patchify(img: Tensor, p: int, round_out: bool) -> Tensor:
+def _pair(p):
+    return (int(p[0]), int(p[1])) if isinstance(p, (tuple, list)) else (int(p), int(p))
+
+
+def patchify(img: Tensor, p, round_out: bool) -> Tensor:
+    """p: patch side or (height, width)"""
     _req(img, "img")
     B, C, H, W = img.shape
-    out = torch.empty(B * (H // p) * (W // p), C * p * p, device=img.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_patchify(_p(img), _p(out), B, C, H, W, p, int(round_out), _stream()), "patchify")
+    ph, pw = _pair(p)
+    out = torch.empty(B * (H // ph) * (W // pw), C * ph * pw, device=img.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_patchify(_p(img), _p(out), B, C, H, W, ph, pw, int(round_out), _stream()), "patchify")
     return out
 
 
-def unpatchify(tok: Tensor, bias: Optional[Tensor], B: int, C: int, H: int, W: int, p: int) -> Tensor:
+def unpatchify(tok: Tensor, bias: Optional[Tensor], B: int, C: int, H: int, W: int, p) -> Tensor:
     _req(tok, "tok"); _req(bias, "bias")
+    ph, pw = _pair(p)
     img = torch.empty(B, C, H, W, device=tok.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b200vq_unpatchify(_p(tok), _p(bias), _p(img), B, C, H, W, p, _stream()), "unpatchify")
+    _lib.check(_lib.lib().b200vq_unpatchify(_p(tok), _p(bias), _p(img), B, C, H, W, ph, pw, _stream()), "unpatchify")
     return img
 
 

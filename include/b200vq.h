@@ -138,10 +138,12 @@ int b200vq_vq_embed(const float* E, const long long* codes, float* out, int M, i
                     void* stream);
 
 /* ---- re-layout / reductions ------------------------------------------------------------------------*/
-/* [B,C,H,W] -> [B*(H/p)*(W/p), C*p*p], patch vector ordered (c,ph,pw) (layers.py:168-171) */
-int b200vq_patchify(const float* img, float* patches, int B, int C, int H, int W, int p, int round_out, void* stream);
+/* [B,C,H,W] -> [B*(H/ph)*(W/pw), C*ph*pw], patch vector ordered (c,row,col) (layers.py:157-171); pw % 4 == 0 */
+int b200vq_patchify(const float* img, float* patches, int B, int C, int H, int W, int ph, int pw, int round_out,
+                    void* stream);
 /* inverse, adding bias[c] if non-NULL (ConvTranspose2d bias, layers.py:204) */
-int b200vq_unpatchify(const float* tokens, const float* bias, float* img, int B, int C, int H, int W, int p, void* stream);
+int b200vq_unpatchify(const float* tokens, const float* bias, float* img, int B, int C, int H, int W, int ph, int pw,
+                      void* stream);
 size_t b200vq_colsum_workspace_bytes(int N);
 /* out[n] = sum_m X[m,n] (bias gradients) */
 int b200vq_colsum(const float* X, long long ld, int M, int N, float* out, void* workspace, size_t ws_bytes, void* stream);

@@ -424,3 +424,33 @@ def test_frozen_model_backward_skips_parameter_gradients():
     n0 = etb.ops.launch_count()
     enc(img).square().mean().backward()
     assert n_frozen < etb.ops.launch_count() - n0
+
+
+def test_non_square_patches_match_the_reference_modules():
+    """reference layers.py:157-166 accepts (height, width) patches; checked against the vendored reference modules
+    (oracle/_ref, built by oracle/build_ref.py) on the CPU"""
+    import importlib.util
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "enhancing_ref")
+    if not os.path.exists(os.path.join(ref_dir, "layers.py")):
+        pytest.skip("oracle/_ref not present")
+    if not hasattr(np, "float"):
+        np.float = float
+    spec = importlib.util.spec_from_file_location("enhancing_ref_ns.layers", os.path.join(ref_dir, "layers.py"))
+    RL = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RL)
+    etb.set_precision("parity")
+    torch.manual_seed(0)
+    kw = dict(image_size=(32, 48), patch_size=(8, 4), dim=64, depth=1, heads=2, mlp_dim=128, dim_head=32)
+    ref_e, ref_d = RL.ViTEncoder(**kw), RL.ViTDecoder(**kw)
+    enc, dec = etb.ViTEncoder(**kw), etb.ViTDecoder(**kw)
+    enc.load_state_dict(ref_e.state_dict(), strict=True); dec.load_state_dict(ref_d.state_dict(), strict=True)
+    enc.cuda(); dec.cuda()
+    img = torch.rand(2, 3, 32, 48)
+    h_ref = ref_e(img)
+    rec_ref = ref_d(h_ref)
+    h = enc(img.cuda())
+    assert h.shape == h_ref.shape == (2, 48, 64)
+    assert relmax(h.cpu(), h_ref.detach()) < 5e-5
+    assert relmax(dec(h).cpu(), rec_ref.detach()) < 5e-5
+    with pytest.raises(NotImplementedError, match="multiple of 4"):
+        etb.ViTEncoder(image_size=30, patch_size=6, dim=64, depth=1, heads=2, mlp_dim=64)
