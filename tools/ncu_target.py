@@ -1,5 +1,5 @@
 """Tiny launch scripts for `ncu --set full` captures (one kernel family per invocation):
-    python tests/ncu_target.py gemm|gemm2|gemm16|attn|attn16|vq|ln"""
+    python tools/ncu_target.py gemm|gemm2|gemm16|attn|attn16|vq|ln"""
 import sys
 
 import torch

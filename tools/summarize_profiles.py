@@ -2,13 +2,13 @@
 """Turn the raw GPU evidence a `gpurun` trip leaves under gpurun_out/ into the tracked summaries under
 profiles/ (the .ncu-rep files themselves are too big to commit).
 
-    python tools/summarize_profiles.py [--round r01] [--src gpurun_out] [--dst profiles]
+    python tools/summarize_profiles.py [--round r02] [--src gpurun_out/evidence] [--dst profiles]
 
 inputs (all optional, whatever exists is summarised):
     <src>/bench.json              bench.py line of the default run          -> <round>_bench_1gpu.json
     <src>/launches.csv            ncu --metrics gpu__time_duration.sum --csv of the same bench command
                                                                             -> <round>_launches_bench_B128.csv, <round>_launch_shares.txt
-    <src>/prof_{gemm2,attn,vq,ln}.ncu-rep   ncu --set full captures of tests/ncu_target.py
+    <src>/prof_{gemm16,attn16,vq,ln}.ncu-rep   ncu --set full captures of tools/ncu_target.py
                                                                             -> <round>_ncu_*.txt
 """
 from __future__ import annotations
@@ -43,24 +43,21 @@ METRICS = [
 ]
 
 HEADERS = {
-    "gemm2": "# gemm_tf32_kernel<256,2,0,0>  to_qkv forward shape M=131072 N=2304 K=768 (round_out=1)\n"
-             "# algorithmic: 463.9 GFLOP, 1.618 GB (A 403 MB + B 7 MB + C 1208 MB).  traffic = dram read+write below.  python tests/ncu_target.py gemm2\n",
-    "attn": "# attention kernels, B=32 N=1024 heads=12 dh=64 (python tests/ncu_target.py attn)\n"
-            "# algorithmic flops: fwd 4*B*H*N*N*dh = 103 GFLOP; bwd 10*B*H*N*N*dh = 258 GFLOP (dKV 6, dQ 4 GEMM-units of 2*N*N*dh)\n",
-    "vq": "# vq_fwd_kernel 131072 tokens x 8192 codes x 32 dims (python tests/ncu_target.py vq)\n"
+    "gemm16": "# gemm_tc_kernel<KIND=f16, BN=256, CG=2>: to_qkv forward shape M=131072 N=2304 K=768 with fp16 output, and net.2 forward\n"
+              "# shape M=131072 N=768 K=3072 with fp32 output (python tools/ncu_target.py gemm16).\n"
+              "# algorithmic: 463.9 GFLOP / 0.809 GB (A 201 MB + B 3.5 MB + C 604 MB) and 618.5 GFLOP / 1.213 GB (A 805 + B 4.7 + C 403 MB).\n"
+              "# traffic = dram read+write below.\n",
+    "attn16": "# fp16 attention core, B=32 N=1024 heads=12 dh=64 (python tools/ncu_target.py attn16)\n"
+              "# algorithmic flops: fwd 4*B*H*N*N*dh = 103 GFLOP; bwd 10*B*H*N*N*dh = 258 GFLOP (dKV 6, dQ 4 GEMM-units of 2*N*N*dh executed: 14)\n",
+    "vq": "# vq_fwd_kernel 131072 tokens x 8192 codes x 32 dims (python tools/ncu_target.py vq)\n"
           "# algorithmic: 68.7 GFLOP fp32 FMA, 34.6 MB (z in, z_q out, idx out, codebook)\n",
-    "ln": "# ln_fwd / ln_bwd kernels M=131072 D=768 (python tests/ncu_target.py ln)\n"
+    "ln": "# ln_fwd / ln_bwd kernels M=131072 D=768 (python tools/ncu_target.py ln)\n"
           "# algorithmic bytes: fwd 805 MB (read x, write y), bwd 1611 MB (read dy, x, dres; write dx)\n",
 }
-# captures that predate later kernel changes (the round's GPU budget ran out before they could be redone)
-STALE_NOTES = {
-    "attn": "# NOTE: this capture predates the TMA-store epilogues and the pipelined forward softmax (commit e159a95 and later).\n"
-            "#       Current per-launch times at B=128 from the round-end launch list (r01_launch_shares.txt): fwd 906 us, dKV 1505 us,\n"
-            "#       dQ 1261 us (this capture's build: 1223 / 2145 / 1387 us); at B=64 under CUDA events: fwd 0.445 ms, bwd 1.421 ms.\n",
-    "ln": "# NOTE: captured after the shared-memory-accumulator rewrite of ln_bwd but before the optional third accumulator\n"
-          "#       (colsum of dx); round-end launch list: ln_bwd 256 us in the training step (NACC=3 variant), ln_fwd 126 us.\n",
-}
-OUT_NAMES = {"gemm2": "ncu_gemm_cg2", "attn": "ncu_attention", "vq": "ncu_vq", "ln": "ncu_layernorm"}
+STALE_NOTES = {}
+OUT_NAMES = {"gemm16": "ncu_gemm_f16", "attn16": "ncu_attention_f16", "vq": "ncu_vq", "ln": "ncu_layernorm"}
+METRICS += ["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]
 
 
 def ncu_raw(rep: str):
@@ -116,7 +113,7 @@ def summarise_launches(src: str, dst: str, rnd: str) -> None:
         short = re.sub(r"<.*", "", name.replace("void ", ""))
         tot[short] += ns
         cnt[short] += 1
-        m = re.search(r"gemm_tf32_kernel<(\d+), (\d+), (\d+), (\d+)>", name)
+        m = re.search(r"gemm_tc_kernel<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)>", name)
         if m:
             gemm[m.groups()].append(ns / 1e3)
     total = sum(tot.values())
@@ -126,15 +123,15 @@ def summarise_launches(src: str, dst: str, rnd: str) -> None:
         try:
             j = json.loads(open(bjson).read().strip().splitlines()[-1])
             bench_line = (f"# bench.py (same command, NOT under ncu): {j['value']:.1f} {j['unit']}, {j['ms_per_step']:.1f} ms/step; live CUDA-event share "
-                          f"of the step spent in gemm_tf32_kernel: {j.get('roofline', {}).get('share_of_step')}\n")
+                          f"of the step spent in gemm_tc_kernel: {j.get('roofline', {}).get('share_of_step')}\n")
         except Exception:
             pass
-    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none -s 2800 -c 1000 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n",
-             "# (B=128/GPU, base config).  ~1000 launches = a little over one fwd+bwd step; per-launch times are cold-cache and\n",
+    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none -s 2540 -c 860 python bench.py --steps 1 --warmup 3 --extras ''\n",
+             "# (B=128/GPU, base config, fp16 data path).  ~860 launches = one fwd+bwd step; per-launch times are cold-cache and\n",
              "# serialised: compare SHARES with bench.py's live numbers, not absolutes.\n", bench_line]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         lines.append(f"{100 * v / total:6.2f}%  launches={cnt[k]:4d}  avg={v / cnt[k] / 1e3:9.1f} us  {k}\n")
-    lines.append("\n# gemm_tf32_kernel<BN, CG, AMAJ, BMAJ> launches by duration (us rounded to 20: count)\n")
+    lines.append("\n# gemm_tc_kernel<KIND, BN, CG, AMAJ, BMAJ, OUT16> launches by duration (us rounded to 20: count)\n")
     for k, v in sorted(gemm.items(), key=lambda kv: -sum(kv[1])):
         hist = collections.Counter(int(round(x / 20.0) * 20) for x in v)
         lines.append(f"{k} n={len(v)} total={sum(v) / 1e3:.1f} ms  {sorted(hist.items())}\n")
@@ -146,8 +143,8 @@ def summarise_launches(src: str, dst: str, rnd: str) -> None:
 
 def main() -> int:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--round", default="r01")
-    ap.add_argument("--src", default="gpurun_out")
+    ap.add_argument("--round", default="r02")
+    ap.add_argument("--src", default="gpurun_out/evidence")
     ap.add_argument("--dst", default="profiles")
     a = ap.parse_args()
     os.makedirs(a.dst, exist_ok=True)
@@ -156,7 +153,7 @@ def main() -> int:
         shutil.copy(b, os.path.join(a.dst, f"{a.round}_bench_1gpu.json"))
         print("copied bench.json")
     summarise_launches(a.src, a.dst, a.round)
-    for tag in ("gemm2", "attn", "vq", "ln"):
+    for tag in ("gemm16", "attn16", "vq", "ln"):
         summarise_rep(tag, a.src, a.dst, a.round)
     return 0
 
