@@ -170,3 +170,15 @@ def test_unchanged_lightning_module_constructs_with_patched_classes(monkeypatch)
     mod.Encoder = None
     etb.patch(mod)
     assert mod.Encoder is etb.ViTEncoder
+    # ... and makes every ViTVQ built afterwards carry QuantLinear pre/post_quant that share the nn.Linear parameters
+    # and state-dict keys (vitvqgan.py:38-39); patching twice does not wrap twice
+    etb.patch(mod)
+    assert mod.ViTVQ.__init__.__wrapped__.__name__ == "__init__" and not hasattr(mod.ViTVQ.__init__.__wrapped__, "__wrapped__")
+    model2 = mod.ViTVQ(image_key="image", image_size=32, patch_size=8, encoder=enc, decoder=enc,
+                       quantizer=AttrDict(embed_dim=32, n_embed=128), loss=AttrDict())
+    assert isinstance(model2.pre_quant, etb.QuantLinear) and isinstance(model2.post_quant, etb.QuantLinear)
+    assert set(model2.state_dict()) == keys
+    model2.load_state_dict(model.state_dict(), strict=True)
+    plain = torch.nn.Linear(64, 32)
+    fused = etb.QuantLinear.from_linear(plain)
+    assert fused.weight is plain.weight and fused.bias is plain.bias and isinstance(fused, torch.nn.Linear)
