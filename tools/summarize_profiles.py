@@ -110,7 +110,7 @@ def summarise_launches(src: str, dst: str, rnd: str) -> None:
             continue
         ns = float(r["Metric Value"])
         name = r["Kernel Name"]
-        short = re.sub(r"<.*", "", name.replace("void ", ""))
+        short = re.sub(r"[<(].*", "", name.replace("void ", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", ""))
         tot[short] += ns
         cnt[short] += 1
         m = re.search(r"gemm_tc_kernel<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)>", name)
