@@ -325,24 +325,26 @@ def main():
 
     def make_step(model, net, comm_events=None):
         params = list(model.parameters())
+        flat = etb.FlatGradients(params) if (world > 1 and not args.ddp) else None
 
         def step(x, second_forward=False):
-            for p in params:
-                p.grad = None
+            if flat is not None:
+                flat.zero_()                   # .grad = views into one flat buffer: the all-reduce needs no bucket copies
+            else:
+                for p in params:
+                    p.grad = None
             if second_forward:                 # the reference training_step runs forward twice per batch (vitvqgan.py:101-127)
                 with torch.no_grad():
                     net(x)
             loss = net(x)
             loss.backward()
-            if world > 1 and not args.ddp:
+            if flat is not None:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                flat.allreduce()
+                e.record()
                 if comm_events is not None:
-                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record()
-                    etb.allreduce_gradients(params)
-                    e.record()
                     comm_events.append((s, e))
-                else:
-                    etb.allreduce_gradients(params)
             return loss
         return step
 

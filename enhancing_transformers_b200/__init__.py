@@ -11,13 +11,13 @@ from . import _lib, configs, functional, ops  # noqa: F401
 from .functional import get_precision, invalidate_shadows, set_precision  # noqa: F401
 from .layers import (Attention, FeedForward, PreNorm, QuantLinear, Transformer, ViTDecoder, ViTEncoder,  # noqa: F401
                      sincos_table)
-from .parallel import allreduce_gradients  # noqa: F401
+from .parallel import FlatGradients, allreduce_gradients  # noqa: F401
 from .quantizers import BaseQuantizer, VectorQuantizer  # noqa: F401
 
 __version__ = "0.2.0"
 __all__ = ["ViTEncoder", "ViTDecoder", "VectorQuantizer", "BaseQuantizer", "Transformer", "Attention", "FeedForward",
            "PreNorm", "QuantLinear", "patch", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
-           "get_precision", "invalidate_shadows", "allreduce_gradients", "ops", "functional", "configs"]
+           "get_precision", "invalidate_shadows", "allreduce_gradients", "FlatGradients", "ops", "functional", "configs"]
 
 _REF_PKG = "enhancing.modules.stage1"
 

@@ -93,6 +93,9 @@ vq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ EnT, const 
   float* zz_s = reinterpret_cast<float*>(ee_s) + 2 * kVqTileN;
   int* best_s = reinterpret_cast<int*>(zz_s + kVqTileM);
   float* red_s = reinterpret_cast<float*>(best_s + kVqTileM);
+  // residual / accumulated-code state of the depth loop, parked in shared memory while the distance loop runs: it is only
+  // touched in phases A and C, and keeping its 32 registers live across phase B spilled the 8x8 accumulator tile
+  float4* park = reinterpret_cast<float4*>(red_s + 8);          // [8][256]: rreg[ps] at ps*256 + tid, acc[ps] at (4+ps)*256 + tid
 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * kVqTileM;
@@ -102,12 +105,11 @@ vq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ EnT, const 
   const int tx = tid & 15, ty = tid >> 4;
 
   // residual and accumulated code per (token, 4-float part); z itself is re-read at the end
-  float4 rreg[4], acc[4];
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int tok = m0 + ps * 32 + (tid >> 3);
-    rreg[ps] = tok < M ? *reinterpret_cast<const float4*>(z + (size_t)tok * kVqD + part * 4) : make_float4(1.f, 0.f, 0.f, 0.f);
-    acc[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+    park[ps * kVqThreads + tid] = tok < M ? *reinterpret_cast<const float4*>(z + (size_t)tok * kVqD + part * 4) : make_float4(1.f, 0.f, 0.f, 0.f);
+    park[(4 + ps) * kVqThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int nchunks = (K + kVqTileN - 1) / kVqTileN;
 
@@ -116,7 +118,7 @@ vq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ EnT, const 
 #pragma unroll
     for (int ps = 0; ps < 4; ++ps) {
       float nrm;
-      const float4 rn = normalize8(rreg[ps], nrm, use_norm);
+      const float4 rn = normalize8(park[ps * kVqThreads + tid], nrm, use_norm);
       const int lt = ps * 32 + (tid >> 3);
       zT[part * 4 + 0][lt] = rn.x;
       zT[part * 4 + 1][lt] = rn.y;
@@ -207,14 +209,17 @@ vq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ EnT, const 
       const float4 e = *reinterpret_cast<const float4*>(E + (size_t)code * kVqD + part * 4);
       float nrm, nrm_r;
       const float4 q = normalize8(e, nrm, use_norm);
-      const float4 rn = normalize8(rreg[ps], nrm_r, use_norm);   // same arithmetic as phase A: identical value
+      float4 rr = park[ps * kVqThreads + tid], ac = park[(4 + ps) * kVqThreads + tid];
+      const float4 rn = normalize8(rr, nrm_r, use_norm);   // same arithmetic as phase A: identical value
       const float dx = q.x - rn.x, dy = q.y - rn.y, dz = q.z - rn.z, dw = q.w - rn.w;
       if (tok < M) {
         lsum += dx * dx + dy * dy + dz * dz + dw * dw;
         if (part == 0) idx_out[(size_t)tok * depth + t] = code;
       }
-      rreg[ps].x -= q.x; rreg[ps].y -= q.y; rreg[ps].z -= q.z; rreg[ps].w -= q.w;
-      acc[ps].x += q.x; acc[ps].y += q.y; acc[ps].z += q.z; acc[ps].w += q.w;
+      rr.x -= q.x; rr.y -= q.y; rr.z -= q.z; rr.w -= q.w;
+      ac.x += q.x; ac.y += q.y; ac.z += q.z; ac.w += q.w;
+      park[ps * kVqThreads + tid] = rr;
+      park[(4 + ps) * kVqThreads + tid] = ac;
     }
     lsum = warp_sum(lsum);
     if ((tid & 31) == 0) red_s[tid >> 5] = lsum;
@@ -233,11 +238,12 @@ vq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ EnT, const 
     const int tok = m0 + ps * 32 + (tid >> 3);
     if (tok < M) {
       const float4 zr = *reinterpret_cast<const float4*>(z + (size_t)tok * kVqD + part * 4);
+      const float4 ac = park[(4 + ps) * kVqThreads + tid];
       float4 o;
-      o.x = zr.x + (acc[ps].x - zr.x);
-      o.y = zr.y + (acc[ps].y - zr.y);
-      o.z = zr.z + (acc[ps].z - zr.z);
-      o.w = zr.w + (acc[ps].w - zr.w);
+      o.x = zr.x + (ac.x - zr.x);
+      o.y = zr.y + (ac.y - zr.y);
+      o.z = zr.z + (ac.z - zr.z);
+      o.w = zr.w + (ac.w - zr.w);
       *reinterpret_cast<float4*>(out + (size_t)tok * kVqD + part * 4) = o;
     }
   }
@@ -404,7 +410,8 @@ __global__ void vq_embed_kernel(const float* __restrict__ E, const long long* __
 
 // ---------------------------------------------------------------------------------------------
 constexpr size_t kVqSmemBytes =
-    sizeof(float) * (kVqD * kVqTileM + 2 * kVqD * kVqTileN + 2 * kVqTileN + kVqTileM + kVqTileM + kVqThreads / 32);
+    sizeof(float) * (kVqD * kVqTileM + 2 * kVqD * kVqTileN + 2 * kVqTileN + kVqTileM + kVqTileM + kVqThreads / 32) +
+    sizeof(float4) * 8 * kVqThreads;
 
 size_t vq_workspace_bytes(int M, int K, int depth) {
   const size_t nblk = (M + kVqTileM - 1) / kVqTileM;

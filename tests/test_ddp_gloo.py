@@ -41,10 +41,16 @@ def _worker(rank, world, port, q, flat):
     imgs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1))
     shard = imgs[rank * 2:(rank + 1) * 2]                       # even split, as main.py's DDP does
     if flat:      # the package's own reduction (what bench.py uses on the GPUs): one flat all-reduce after backward
-        from enhancing_transformers_b200.parallel import allreduce_gradients
+        from enhancing_transformers_b200.parallel import FlatGradients, allreduce_gradients
         local = OracleNet(sd)
-        local(shard).backward()
-        allreduce_gradients(local.parameters())
+        if flat == "views":       # .grad are views into one flat buffer, reduced in place
+            fg = FlatGradients(local.parameters())
+            fg.zero_()
+            local(shard).backward()
+            fg.allreduce()
+        else:
+            local(shard).backward()
+            allreduce_gradients(local.parameters())
         names, params = local.names, local.params
     else:
         net = torch.nn.parallel.DistributedDataParallel(OracleNet(sd))
@@ -68,7 +74,7 @@ def _worker(rank, world, port, q, flat):
 import pytest
 
 
-@pytest.mark.parametrize("flat", [False, True], ids=["torch_ddp", "flat_allreduce"])
+@pytest.mark.parametrize("flat", [False, True, "views"], ids=["torch_ddp", "flat_allreduce", "flat_views"])
 def test_sharded_ddp_gradients_equal_single_process(flat):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
