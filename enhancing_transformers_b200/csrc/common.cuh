@@ -132,11 +132,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// arrive on the same-named barrier of CTA `rank` of this cluster
+// arrive on the same-named barrier of CTA `rank` of this cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive does: the arrival only hands TMEM back to the MMA warp, which tcgen05.fence::before_thread_sync has
+// already ordered; a `.release.cluster` arrive compiled to MEMBAR.ALL + ERRBAR per tile per epilogue warp of the follower
+// CTA (16 % of the GEMM's stall samples, profiles/r02_ncu_gemm_f16.txt).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// Arrivals that only hand a TMEM buffer back (the reads were completed by tcgen05.wait::ld and ordered by
+// tcgen05.fence::before_thread_sync) need no memory ordering at all: relaxed, so that no MEMBAR waits for unrelated
+// outstanding loads of the arriving warp.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // Spin on a phase parity.  A deadlocked pipeline would otherwise hang the GPU until the
 // watchdog kills the box, so after ~4e9 cycles (seconds) the kernel traps instead.

@@ -395,8 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 1 || leader) mbar_arrive(&tmem_empty[acc]);
-        else                   mbar_arrive_remote(&tmem_empty[acc], 0);
+        if (CG == 1 || leader) mbar_arrive_relaxed(&tmem_empty[acc]);
+        else                   mbar_arrive_remote_relaxed(&tmem_empty[acc], 0);
       }
     }
     if (lane == 0) bulk_wait_group_read<0>();   // smem must outlive the last stores' reads
