@@ -129,7 +129,7 @@ struct FwdParams {
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   constexpr int NST = kFwdStages;
   uint8_t* Qs = smem;                              // [2]: the next item's Q tile loads while this item computes
   uint8_t* Ks = smem + 2 * kTile128;               // [NST]
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   constexpr int NST = kBwdStages;
   uint8_t* KVs = smem;                        // [2] item buffers [K128 | V128]: the next item's tiles load while this one computes
   uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [Q64 | dO64]
@@ -524,6 +524,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const int sub = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
+    float* bc = reinterpret_cast<float*>(bars + 64) + (warp - 2) * 32;     // this warp's lse / delta broadcast slot
     uint32_t t_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       const int kt = w % p.tiles128;
@@ -531,33 +532,44 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       const int h = bh % p.heads, b = bh / p.heads;
       const float* lb = p.lse + ((long long)b * p.heads + h) * p.N;
       const float* eb = p.delta + ((long long)b * p.heads + h) * p.N;
-      // per-column lse / delta: lane l keeps the values of query column sub*16 + (l & 15) of the current sub-tile in
-      // registers (fetched one sub-tile ahead) and the 16 columns are broadcast with warp shuffles (see attention_tc.cu)
+      // per-column lse / delta: the 16 query columns of this warp's slice are the same for all 32 key rows, so the warp
+      // stages them (lanes 0..15: lse * log2e, lanes 16..31: delta; fetched one sub-tile ahead) in a 32-float slot of
+      // shared memory and every thread reads them back as eight broadcast 128-bit loads -- the warp-shuffle broadcast
+      // this replaces cost two SHFL per score (ncu: 32 of the 260 issue slots a warp spent per sub-tile).
+      const bool is_l = lane < 16;
+      const float* src = is_l ? lb : eb;
       const int qcol = sub * 16 + (lane & 15);
-      float raw_l = 0.f, raw_e = 0.f;
+      float raw = 0.f;
       bool nvalid = qcol < p.N;
-      if (nvalid) { raw_l = lb[qcol]; raw_e = eb[qcol]; }
+      if (nvalid) raw = src[qcol];
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it % kTB;
-        const float myL = nvalid ? raw_l * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
-        const float myE = nvalid ? raw_e : 0.f;
+        bc[lane] = is_l ? (nvalid ? raw * kLog2eF : INFINITY) : (nvalid ? raw : 0.f);   // +inf -> P = 0 for padded queries
         {
           const int qi = (i + 1) * 64 + qcol;
           nvalid = i + 1 < NS && qi < p.N;
-          if (nvalid) { raw_l = lb[qi]; raw_e = eb[qi]; }
+          if (nvalid) raw = src[qi];
         }
         mbar_wait(&s_full[s], (t_it / kTB) & 1);
         tcgen05_fence_after();
+        __syncwarp();
         const int col = s * 64 + sub * 16;
         uint32_t v[16], g[16];
         tmem_ld_32x16(tmem_base + lane_off + col, v);
         tmem_ld_32x16(tmem_base + lane_off + kColDP + col, g);
+        float4 L4[4], E4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          L4[j] = reinterpret_cast<const float4*>(bc)[j];
+          E4[j] = reinterpret_cast<const float4*>(bc)[4 + j];
+        }
         tmem_ld_wait();
         uint32_t pp[8], ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float L0 = __shfl_sync(0xffffffffu, myL, 2 * j), L1 = __shfl_sync(0xffffffffu, myL, 2 * j + 1);
-          const float E0 = __shfl_sync(0xffffffffu, myE, 2 * j), E1 = __shfl_sync(0xffffffffu, myE, 2 * j + 1);
+          const float4 Lq = L4[j >> 1], Eq = E4[j >> 1];
+          const float L0 = (j & 1) ? Lq.z : Lq.x, L1 = (j & 1) ? Lq.w : Lq.y;
+          const float E0 = (j & 1) ? Eq.z : Eq.x, E1 = (j & 1) ? Eq.w : Eq.y;
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
           const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -L1));
           pp[j] = pack_h2(p0, p1);
@@ -601,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
                        const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   constexpr int NST = kBwdStages;
   uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128]
   uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [K64 | V64]
@@ -753,11 +765,16 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         uint32_t ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
-          if (2 * j >= kv_left) p0 = 0.f;            // ragged last tile: padded key columns contribute nothing
-          if (2 * j + 1 >= kv_left) p1 = 0.f;
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
+        }
+        if (kv_left < 16) {                            // ragged last tile (warp-uniform): padded key columns contribute nothing
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (2 * j >= kv_left) ds[j] = 0u;
+            else if (2 * j + 1 >= kv_left) ds[j] &= 0xffffu;
+          }
         }
         tmem_st_32x8(tmem_base + lane_off + kColDP + col, ds);
         tmem_st_wait();
@@ -862,7 +879,7 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale;
-  constexpr int smem = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + 1024;
+  constexpr int smem = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 128 + 1024;
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem);
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem);
   const int grid = persistent_grid(p.total_items);

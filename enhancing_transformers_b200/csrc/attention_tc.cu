@@ -129,7 +129,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   constexpr int TILE_BYTES = 128 * DH * 4;    // one Q / K / V tile
   constexpr int KBLK_BYTES = 128 * 128;       // one k-block (or one MN atom of V): 128 rows x 128 B
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + TILE_BYTES;            // [2]
   uint8_t* Vs = smem + 3 * TILE_BYTES;        // [2]
@@ -500,7 +500,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
   constexpr int T64 = 64 * DH * 4;     // one 64-row operand copy
   constexpr int KBLK128 = 128 * 128, KBLK64 = 64 * 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* Ks = smem;
   uint8_t* Vs = smem + T128;
   uint8_t* St = smem + 2 * T128;        // stage s at St + s*4*T64: [QK | DK | QM | DM]
@@ -761,7 +761,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   constexpr int T64 = 64 * DH * 4;
   constexpr int KBLK128 = 128 * 128, KBLK64 = 64 * 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* Qs = smem;
   uint8_t* Ds = smem + T128;
   uint8_t* St = smem + 2 * T128;        // stage s at St + s*3*T64: [KK | VK | KM]

@@ -70,6 +70,9 @@ inline int make_tensor_map_f32(CUtensorMap* out, const float* ptr, int rank, con
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 1024-byte alignment of the dynamic shared-memory base (SWIZZLE_128B atoms) as pointer arithmetic on the __shared__
+// symbol: a round trip through uintptr_t loses the address space and every later access becomes a generic LD / ST.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 // One lane of a fully converged warp (the lowest).  Role warps keep their control flow warp-uniform
 // and gate only the issuing instructions with this: the compiler then keeps descriptors and loop
@@ -152,12 +155,13 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-// Spin on a phase parity.  A deadlocked pipeline would otherwise hang the GPU until the
-// watchdog kills the box, so after ~4e9 cycles (seconds) the kernel traps instead.
+// Spin on a phase parity.  A deadlocked pipeline would otherwise hang the GPU until the watchdog kills the box, so
+// after 2^28 failed probes (each try_wait suspends the thread for a hardware-defined slice: seconds in total) the kernel
+// traps instead.  The loop body is the probe, one add and one compare: spinning producer / issuer warps share their
+// scheduler's issue slots with the epilogue and softmax warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
+  const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -167,8 +171,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (it == 64) t0 = clock64();
-    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    if (it == (1u << 28)) __trap();
   }
 }
 
@@ -394,10 +397,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
 }
 // two fp32 -> packed fp16x2 (round to nearest), saturating at +-65504 instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;      // one F2FP.SATFINITE: a -> low half, b -> high half
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 #endif  // __CUDACC__
 
