@@ -374,7 +374,8 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 // =============================================================================================
 struct BwdParams {
   const float* lse;
-  const float* delta;
+  const float* delta;    // rowsum(dO * O): written by the dQ kernel (delta_w), read by the dKV kernel that runs after it
+  float* delta_w;
   int N, heads, tiles128, sub64, total_items;
   float scale;
 };
@@ -611,12 +612,14 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
-                       const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
+                       const __grid_constant__ CUtensorMap tmO128, const __grid_constant__ CUtensorMap tmQKV64,
+                       const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   constexpr int NST = kBwdStages;
-  uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128]
-  uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [K64 | V64]
+  constexpr int kItem = 3 * kTile128;
+  uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128 | O128] (O only feeds delta = rowsum(dO * O))
+  uint8_t* St = smem + 2 * kItem;             // ring stage r at St + r * 2 * kTile64: [K64 | V64]
   uint8_t* obox = St + NST * 2 * kTile64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
   uint64_t* q_full = bars + 0;     // [2]
@@ -629,10 +632,11 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   uint64_t* kv_full = bars + 15;          // [NST]
   uint64_t* kv_empty = kv_full + NST;     // [NST] two arrivals (score MMAs, dQ MMAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_full + 2 * NST);
+  float* xch = reinterpret_cast<float*>(bars + 64);   // [2][4][128] partial delta exchange (double buffered by item)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmQKV64);
+    tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmO128); tma_prefetch_desc(&tmQKV64);
     for (int s = 0; s < NST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps); mbar_init(&sfree[s], 1); }
@@ -656,9 +660,10 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const int ib = item_it & 1;
       mbar_wait(&q_empty[ib], ((item_it >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&q_full[ib], 2 * kTile128);
-        tma_load_3d(QDs + ib * 2 * kTile128, &tmQKV128, &q_full[ib], h * DH, qt * 128, b);
-        tma_load_3d(QDs + ib * 2 * kTile128 + kTile128, &tmDO128, &q_full[ib], h * DH, qt * 128, b);
+        mbar_arrive_expect_tx(&q_full[ib], kItem);
+        tma_load_3d(QDs + ib * kItem, &tmQKV128, &q_full[ib], h * DH, qt * 128, b);
+        tma_load_3d(QDs + ib * kItem + kTile128, &tmDO128, &q_full[ib], h * DH, qt * 128, b);
+        tma_load_3d(QDs + ib * kItem + 2 * kTile128, &tmO128, &q_full[ib], h * DH, qt * 128, b);
       }
       __syncwarp();
       for (int i = 0; i < NS; ++i, ++sub_it) {
@@ -683,7 +688,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       const int ib = item_it & 1;
       mbar_wait(&q_full[ib], (item_it >> 1) & 1);
-      const uint64_t qd = desc_advance(qd0, ib * 2 * kTile128);
+      const uint64_t qd = desc_advance(qd0, ib * kItem);
       const uint64_t dd = desc_advance(qd, kTile128);
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it % kTB;
@@ -751,7 +756,37 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const int row = qt * 128 + q * 32 + lane;
       const long long sidx = ((long long)b * p.heads + h) * p.N + row;
       const float lse2 = row < p.N ? p.lse[sidx] * kLog2eF : INFINITY;
-      const float dl = row < p.N ? p.delta[sidx] : 0.f;
+      // delta = rowsum(dO * O) of this thread's query row, from the item's dO and O tiles in shared memory (128-byte rows,
+      // 16-byte chunks XOR-swizzled by row & 7): each of the four threads of a row takes 16 of the 64 columns and the
+      // partial sums meet in shared memory under the lane quarter's named barrier.  Rows >= N are zero-filled by TMA.
+      float dl;
+      {
+        const int ib = item_it & 1;
+        mbar_wait(&q_full[ib], (item_it >> 1) & 1);
+        const int r = q * 32 + lane;
+        const uint8_t* dOt = QDs + ib * kItem + kTile128 + r * 128;
+        const uint8_t* Ot = dOt + kTile128;
+        float acc = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int off = ((sub * 2 + ch) ^ (r & 7)) << 4;
+          const uint4 a = *reinterpret_cast<const uint4*>(dOt + off);
+          const uint4 o = *reinterpret_cast<const uint4*>(Ot + off);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+            const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&ow[k]));
+            acc = fmaf(fa.x, fo.x, acc);
+            acc = fmaf(fa.y, fo.y, acc);
+          }
+        }
+        float* xs = xch + ib * 512;
+        xs[sub * 128 + r] = acc;
+        quad_bar(q);
+        dl = (xs[r] + xs[128 + r]) + (xs[256 + r] + xs[384 + r]);
+        if (sub == 0 && row < p.N) p.delta_w[sidx] = dl;
+      }
       for (int i = 0; i < NS; ++i, ++t_it) {
         const int s = t_it % kTB;
         mbar_wait(&s_full[s], (t_it / kTB) & 1);
@@ -853,40 +888,40 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   return 0;
 }
 
-int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
-                    cudaStream_t stream);
-
 // dout fp16 (carrying the gradient scale), out fp16; dqkv fp16 (same scale); delta scratch fp32 [B*heads*N]
 int attention_f16_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* delta, int B, int N,
                            int heads, int dh, float scale, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == DH, "attention_f16: dim_head must be 64 (got %d)", dh);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "attention: qkv/dout/dqkv must be 16-byte aligned");
-  int rc = attention_delta(out, 1, dout, 1, delta, B, N, heads, dh, stream);
-  if (rc) return rc;
+                     (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "attention: qkv/out/dout/dqkv must be 16-byte aligned");
+  int rc;
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
-  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmOut, tmOut16;
+  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmO128, tmOut, tmOut16;
   if ((rc = make_tile_map(&tmQKV128, qkv, ld, N, B, 128))) return rc;
   if ((rc = make_tile_map(&tmQKV64, qkv, ld, N, B, 64))) return rc;
   if ((rc = make_tile_map(&tmDO128, dout, inner, N, B, 128))) return rc;
   if ((rc = make_tile_map(&tmDO64, dout, inner, N, B, 64))) return rc;
+  if ((rc = make_tile_map(&tmO128, out, inner, N, B, 128))) return rc;
   if ((rc = make_store_map(&tmOut, dqkv, ld, N, B, 32))) return rc;
   if ((rc = make_store_map(&tmOut16, dqkv, ld, N, B, 16))) return rc;
   BwdParams p;
-  p.lse = lse; p.delta = delta; p.N = N; p.heads = heads;
+  p.lse = lse; p.delta = delta; p.delta_w = delta; p.N = N; p.heads = heads;
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale;
-  constexpr int smem = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 128 + 1024;
-  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem);
-  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem);
+  constexpr int smem_kv = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 128 + 1024;
+  constexpr int smem_q = 6 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + 1024 * 4 + 1024;
+  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem_kv);
+  B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem_q);
   const int grid = persistent_grid(p.total_items);
-  attn_bwd_dkv_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmQKV64, tmDO64, tmOut, p);
-  B200_LAUNCH_OK("attn_bwd_dkv_f16_kernel");
-  attn_bwd_dq_f16_kernel<<<grid, kThreads, smem, stream>>>(tmQKV128, tmDO128, tmQKV64, tmOut16, p);
+  // dQ first: it also produces delta = rowsum(dO * O) from the O tile it loads next to dO (no separate pass over dO and O)
+  attn_bwd_dq_f16_kernel<<<grid, kThreads, smem_q, stream>>>(tmQKV128, tmDO128, tmO128, tmQKV64, tmOut16, p);
   B200_LAUNCH_OK("attn_bwd_dq_f16_kernel");
+  attn_bwd_dkv_f16_kernel<<<grid, kThreads, smem_kv, stream>>>(tmQKV128, tmQKV64, tmDO64, tmOut, p);
+  B200_LAUNCH_OK("attn_bwd_dkv_f16_kernel");
   return 0;
 }
 

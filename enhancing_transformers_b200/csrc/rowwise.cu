@@ -180,16 +180,35 @@ __global__ void colpart_reduce_kernel(const float* __restrict__ part, int nparts
   out[j] = a;
 }
 
-// part is [nparts][nacc][D] -> dgamma[D], dbeta[D] (, dxsum[D])
-__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, int nacc, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ dxsum) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nacc * D) return;
-  float a = 0.f;
-  for (int i = 0; i < nparts; ++i) a += part[(size_t)i * nacc * D + j];
-  if (j < D) dgamma[j] = a;
-  else if (j < 2 * D) dbeta[j - D] = a;
-  else dxsum[j - 2 * D] = a;
+// part is [nparts][nacc][D] -> dgamma[D], dbeta[D] (, dxsum[D]).  A CTA owns 32 columns; its 8 warps take every 8th
+// partial (independent, coalesced 128-byte loads) and meet in shared memory: a chain of nparts / 8 loads per thread
+// instead of nparts (the one-thread-per-column version took 31 us for 296 partials, ncu r02).
+__global__ void __launch_bounds__(256)
+ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, int nacc, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dxsum) {
+  __shared__ float sm[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const int total = nacc * D;
+  float a0 = 0.f, a1 = 0.f;
+  if (j < total) {
+    int i = ty;
+    for (; i + 8 < nparts; i += 16) {
+      a0 += part[(size_t)i * total + j];
+      a1 += part[(size_t)(i + 8) * total + j];
+    }
+    if (i < nparts) a0 += part[(size_t)i * total + j];
+  }
+  sm[ty][tx] = a0 + a1;
+  __syncthreads();
+  if (ty == 0 && j < total) {
+    float a = sm[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) a += sm[w][tx];
+    if (j < D) dgamma[j] = a;
+    else if (j < 2 * D) dbeta[j - D] = a;
+    else dxsum[j - 2 * D] = a;
+  }
 }
 
 // column sums of X[M, N] (bias gradients): stage 1 writes part[blockIdx.y][N].
@@ -456,7 +475,7 @@ int layernorm_backward(const float* dy, const float* x, const float* mean, const
                  : ln_bwd_dispatch<2>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream);
   if (rc) return rc;
   B200_LAUNCH_OK("ln_bwd_kernel");
-  ln_param_reduce_kernel<<<(nacc * D + 255) / 256, 256, 0, stream>>>(part, blocks, D, nacc, dgamma, dbeta, dxsum);
+  ln_param_reduce_kernel<<<(nacc * D + 31) / 32, 256, 0, stream>>>(part, blocks, D, nacc, dgamma, dbeta, dxsum);
   B200_LAUNCH_OK("ln_param_reduce_kernel");
   return 0;
 }

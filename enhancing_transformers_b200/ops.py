@@ -119,14 +119,23 @@ def splitk_reduce(part: Tensor, out: Optional[Tensor] = None, alpha: Optional[Te
 
 
 def pick_splits(k_total: int, out_rows: int, out_cols: int, sms: int = 148, k_atom: int = 32) -> int:
-    """split count for a wgrad GEMM: enough (tile x split) work items to fill the SMs twice,
-    each split contracting a multiple of one k-block (32 fp32 / 64 fp16 elements)."""
+    """split count for a wgrad GEMM, by a two-term cost model.  The persistent kernel runs ceil(tiles * splits / sms) waves
+    of 128 x 256 tiles, so the contraction costs flops / (peak * fill of the last wave) (to_qkv's 54 tiles: 4 splits = 1.46
+    waves, 8 splits = 2.92); the partial sums cost one fp32 write and one read per split.  Each split contracts a multiple
+    of one k-block (32 fp32 / 64 fp16 elements) and at least 256 rows."""
     tiles = -(-out_rows // 128) * -(-out_cols // 256)
-    want = max(1, (2 * sms + tiles - 1) // tiles)
+    peak = 1.3e15 if k_atom == 64 else 0.7e15          # kind::f16 / kind::tf32 issue rates (DESIGN.md section 7)
+    t_mma = 2.0 * k_total * out_rows * out_cols / peak
+    best, best_t = 1, float("inf")
     s = 1
-    while s * 2 <= want and k_total % (s * 2 * k_atom) == 0 and k_total // (s * 2) >= 256:
+    while s <= 32 and k_total % (s * k_atom) == 0 and (s == 1 or k_total // s >= 256):
+        work = tiles * s
+        fill = work / (-(-work // sms) * sms)
+        t = t_mma / fill + (8.0 * s * out_rows * out_cols / 6e12 if s > 1 else 0.0)
+        if t < best_t * 0.98:                            # a larger count has to buy at least 2 %
+            best, best_t = s, t
         s *= 2
-    return s
+    return best
 
 
 # ------------------------------------------------------------------------ operand preparation
