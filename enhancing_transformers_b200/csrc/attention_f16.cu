@@ -34,7 +34,17 @@ constexpr int kBoxBytes = kSoftmaxWarps * 2048;   // one 32-row x 64-byte store 
 // cover a full TMA round trip (~1500 cycles from "stage free" to "bytes landed"): with the 2-deep rings inherited from
 // the tf32 kernels every sub-tile waited for its own load (ncu: the softmax warps' top stall is the wait for S).
 constexpr int kFwdStages = 4;      // K and V rings of the forward kernel (128-row tiles)
-constexpr int kBwdStages = 4;      // [Q64 | dO64] / [K64 | V64] rings of the backward kernels
+// Backward rings ([Q64 | dO64] of the dKV kernel, [K64 | V64] of the dQ kernel).  A stage is released by the LAST MMA that
+// reads it (the gradient MMA of its sub-tile, which runs two to three sub-tiles after the score MMA), so of N stages only
+// N - 3 are ahead of the score issuer: with 4 the issuer waited ~370 cycles for every stage (attn16_trace).
+#ifndef ATTN_DKV_STAGES
+#define ATTN_DKV_STAGES 6
+#endif
+#ifndef ATTN_DQ_STAGES
+#define ATTN_DQ_STAGES 5           // the dQ kernel keeps three 128-row item tiles per buffer: one stage fewer fits
+#endif
+constexpr int kDkvStages = ATTN_DKV_STAGES;
+constexpr int kDqStages = ATTN_DQ_STAGES;
 
 // named barrier of the four softmax warps that share TMEM lane quarter q (ids 2..5, 128 threads)
 __device__ __forceinline__ void quad_bar(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 2) : "memory"); }
@@ -61,6 +71,93 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {      // values known to be in fp16 range
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+
+// Development trace (only with -DB200_ATTN16_TRACE, built into a separate .so by `make trace16`): block 0 of the dKV kernel
+// logs (event id, clock64) pairs of the two issuer warps and one softmax warp into shared memory (tools/gpu_probe.py
+// attn16_trace prints the merged timeline).
+#ifdef B200_ATTN16_TRACE
+#ifndef B200_TRACE_SKIP
+#define B200_TRACE_SKIP 320
+#endif
+constexpr int kTraceCap = 64;
+__device__ long long g_trace16[3 * 2 * kTraceCap];
+#define TRACE_DECL                                                                                \
+  __shared__ long long tr_buf[3][2 * kTraceCap]; int tr_n = 0;                                    \
+  for (int i_ = threadIdx.x; i_ < 3 * 2 * kTraceCap; i_ += blockDim.x) (&tr_buf[0][0])[i_] = 0
+#define TRACE(role, ev)                                                                           \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                             \
+      const int k_ = tr_n++ - B200_TRACE_SKIP;                                                    \
+      if (k_ >= 0 && k_ < kTraceCap) { tr_buf[role][2 * k_] = (ev); tr_buf[role][2 * k_ + 1] = clock64(); } \
+    }                                                                                             \
+  } while (0)
+#define TRACE_DUMP()                                                                              \
+  do {                                                                                            \
+    __syncthreads();                                                                              \
+    if (blockIdx.x == 0) for (int i_ = threadIdx.x; i_ < 3 * 2 * kTraceCap; i_ += blockDim.x) g_trace16[i_] = (&tr_buf[0][0])[i_]; \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(role, ev) do {} while (0)
+#define TRACE_DUMP() do {} while (0)
+#endif
+
+// ---- 2^x on the FMA pipe (tools/exp2_poly.py) --------------------------------------------------------------
+// The softmax of all three kernels is bounded by MUFU.EX2 (16 lanes / clk / SM: ncu shows the XU pipe saturated while
+// the exp phase runs and every warp stalled on its queue), while the FMA pipe idles.  A fixed share of each thread's
+// exponentials is therefore evaluated as a degree-4 polynomial (max rel. error 2.7e-6, below the 4.9e-4 of the fp16
+// rounding P gets anyway) with packed f32x2 arithmetic: 11 issue slots per PAIR of values instead of 16 XU cycles.
+//     t = max(x, -126);  r = t + 1.5*2^23 (round to integer n in the low mantissa bits);  f = t - (r - 1.5*2^23)
+//     p = c0 + f (c1 + f (c2 + f (c3 + f c4)));   2^x = as_float(as_int(p) + (as_int(r) << 23))
+#ifndef ATTN_FWD_POLY_PAIRS
+#define ATTN_FWD_POLY_PAIRS 4       // of the 16 pairs a forward thread exponentiates per key tile
+#endif
+#ifndef ATTN_BWD_POLY_PAIRS
+#define ATTN_BWD_POLY_PAIRS 1       // of the 8 pairs a backward thread exponentiates per sub-tile
+#endif
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& y0, float& y1) {
+  constexpr float kMagic = 12582912.f;
+  const unsigned long long t = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const unsigned long long r = f2_add(t, f2_pack(kMagic, kMagic));
+  const unsigned long long nf = f2_add(r, f2_pack(-kMagic, -kMagic));
+  const unsigned long long f = f2_fma(nf, f2_pack(-1.f, -1.f), t);
+  unsigned long long pl = f2_fma(f2_pack(0.00957007f, 0.00957007f), f, f2_pack(0.05591786f, 0.05591786f));
+  pl = f2_fma(pl, f, f2_pack(0.24024746f, 0.24024746f));
+  pl = f2_fma(pl, f, f2_pack(0.6931218f, 0.6931218f));
+  pl = f2_fma(pl, f, f2_pack(0.9999993f, 0.9999993f));
+  float p0, p1, r0, r1;
+  f2_unpack(pl, p0, p1);
+  f2_unpack(r, r0, r1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+// pair index i of n: the polynomial pairs are spread evenly between the MUFU pairs so both pipes stay fed
+template <int POLY, int N>
+__device__ __forceinline__ constexpr bool poly_slot(int i) { return POLY > 0 && ((i + 1) * POLY) / N != (i * POLY) / N; }
+// use_poly is a compile-time constant at every call site once the surrounding loop is unrolled
+__device__ __forceinline__ void ex2_pair(bool use_poly, float x0, float x1, float& y0, float& y1) {
+  if (use_poly) ex2_poly_pair(x0, x1, y0, y1);
+  else { y0 = ex2_approx(x0); y1 = ex2_approx(x1); }
 }
 
 // 32 rows x 32 values -> fp16 (x mul, saturating) -> 32-row x 64-byte un-swizzled box -> one TMA store
@@ -217,8 +314,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int s = s_it & 1;                       // TMEM S buffer
         const uint32_t ph = (s_it >> 1) & 1;
         const int r = s_it % NST;                     // K ring stage
-        mbar_wait(&k_full[r], (s_it / NST) & 1);
-        mbar_wait(&sfree[s], ph ^ 1);
+        mbar_wait2(&k_full[r], (s_it / NST) & 1, &sfree[s], ph ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kd = desc_advance(kd0, r * kTile128);
@@ -242,9 +338,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int s = pv_it & 1;
         const uint32_t ph = (pv_it >> 1) & 1;
         const int r = pv_it % NST;                    // V ring stage
-        mbar_wait(&v_full[r], (pv_it / NST) & 1);
-        mbar_wait(&o_empty[s], ph ^ 1);
-        mbar_wait(&p_full[s], ph);
+        mbar_wait3(&v_full[r], (pv_it / NST) & 1, &o_empty[s], ph ^ 1, &p_full[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t vd = desc_advance(vd0, r * kTile128);
@@ -315,8 +409,8 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         uint32_t pk[16];       // this thread's 32 probabilities as 16 packed fp16 pairs (keys sub*32 + 2i, +1)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a0 = ex2_approx(fmaf(__uint_as_float(v0[2 * i]), c, -mc));
-          const float a1 = ex2_approx(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc));
+          float a0, a1;
+          ex2_pair(poly_slot<ATTN_FWD_POLY_PAIRS, 16>(i), fmaf(__uint_as_float(v0[2 * i]), c, -mc), fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc), a0, a1);
           sum += a0; sum1 += a1;
           pk[i] = pack_h2(a0, a1);
         }
@@ -386,6 +480,7 @@ __device__ __forceinline__ uint32_t packed_a_col(int k) { return (uint32_t)(k * 
 //   S or S^T buffers at columns [0,64) [64,128) [128,192); dP or dP^T buffers at [192,256) [256,320) [320,384);
 //   accumulators at [384,448) (dV or dQ) and [448,512) (dK)
 constexpr int kTB = 3;
+constexpr int kPArrivals = kSoftmaxWarps / 2;     // two groups of eight softmax warps take alternate sub-tiles
 constexpr uint32_t kColDP = 192, kColAcc = 384;
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -393,7 +488,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
                         const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  constexpr int NST = kBwdStages;
+  constexpr int NST = kDkvStages;
   uint8_t* KVs = smem;                        // [2] item buffers [K128 | V128]: the next item's tiles load while this one computes
   uint8_t* St = smem + 4 * kTile128;          // ring stage r at St + r * 2 * kTile64: [Q64 | dO64]
   uint8_t* obox = St + NST * 2 * kTile64;
@@ -410,11 +505,12 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qd_full + 2 * NST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmQKV64); tma_prefetch_desc(&tmDO64);
     for (int s = 0; s < NST; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps); mbar_init(&sfree[s], 1); }
+    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kPArrivals); mbar_init(&sfree[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
@@ -468,8 +564,9 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         const int s = sd_it % kTB;                    // TMEM S^T / dP^T buffer
         const uint32_t ph = (sd_it / kTB) & 1;
         const int r = sd_it % NST;                    // ring stage
-        mbar_wait(&qd_full[r], (sd_it / NST) & 1);
-        mbar_wait(&sfree[s], ph ^ 1);
+        TRACE(0, 100);
+        mbar_wait2(&qd_full[r], (sd_it / NST) & 1, &sfree[s], ph ^ 1);   // probes overlap: each costs ~200 cycles under MMA operand traffic
+        TRACE(0, 102);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qd = desc_advance(qd0, r * 2 * kTile64);
@@ -485,6 +582,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           if (i == NS - 1) umma_commit<1>(&kv_empty[ib]);
         }
         __syncwarp();
+        TRACE(0, 103);
       }
     }
   } else if (warp == kIssuerB) {
@@ -498,8 +596,9 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         const uint32_t ph = (dv_it / kTB) & 1;
         const int r = dv_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        mbar_wait(&qd_full[r], (dv_it / NST) & 1);
-        mbar_wait(&p_full[s], ph);
+        TRACE(1, 110);
+        mbar_wait2(&qd_full[r], (dv_it / NST) & 1, &p_full[s], ph);
+        TRACE(1, 111);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t qmd = desc_advance(qm0, r * 2 * kTile64);
@@ -516,6 +615,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           if (i == NS - 1) umma_commit<1>(acc_full);
         }
         __syncwarp();
+        TRACE(1, 112);
       }
     }
   } else {
@@ -525,7 +625,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const int sub = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale * kLog2eF;
-    float* bc = reinterpret_cast<float*>(bars + 64) + (warp - 2) * 32;     // this warp's lse / delta broadcast slot
+    float* bc = reinterpret_cast<float*>(bars + 64) + (warp - 2) * 64;     // this warp's lse / delta broadcast slot (2 x 32 floats)
     uint32_t t_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
       const int kt = w % p.tiles128;
@@ -537,52 +637,67 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       // stages them (lanes 0..15: lse * log2e, lanes 16..31: delta; fetched one sub-tile ahead) in a 32-float slot of
       // shared memory and every thread reads them back as eight broadcast 128-bit loads -- the warp-shuffle broadcast
       // this replaces cost two SHFL per score (ncu: 32 of the 260 issue slots a warp spent per sub-tile).
-      const bool is_l = lane < 16;
-      const float* src = is_l ? lb : eb;
-      const int qcol = sub * 16 + (lane & 15);
-      float raw = 0.f;
-      bool nvalid = qcol < p.N;
-      if (nvalid) raw = src[qcol];
-      for (int i = 0; i < NS; ++i, ++t_it) {
-        const int s = t_it % kTB;
-        bc[lane] = is_l ? (nvalid ? raw * kLog2eF : INFINITY) : (nvalid ? raw : 0.f);   // +inf -> P = 0 for padded queries
-        {
-          const int qi = (i + 1) * 64 + qcol;
-          nvalid = i + 1 < NS && qi < p.N;
-          if (nvalid) raw = src[qi];
-        }
-        mbar_wait(&s_full[s], (t_it / kTB) & 1);
-        tcgen05_fence_after();
-        __syncwarp();
-        const int col = s * 64 + sub * 16;
-        uint32_t v[16], g[16];
-        tmem_ld_32x16(tmem_base + lane_off + col, v);
-        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, g);
-        float4 L4[4], E4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          L4[j] = reinterpret_cast<const float4*>(bc)[j];
-          E4[j] = reinterpret_cast<const float4*>(bc)[4 + j];
-        }
-        tmem_ld_wait();
+      // Two groups of eight warps take alternate sub-tiles (grp = parity), a warp owning 32 of the 64 query columns as two
+      // 16-column chunks: the second chunk's tcgen05.ld travels while the first is computed, and while one group is in its
+      // exp phase the other is loading / storing -- with all 16 warps on every sub-tile the sub-tile rate was one over a
+      // warp's own ld -> exp -> st -> arrive latency (~1450 cycles, attn16_trace), not the MMA floor (768).
+      const int grp = sub & 1, half = sub >> 1;
+      const int qcol = half * 32 + lane;
+      const uint32_t t_base = item_it * (uint32_t)NS;
+      float rawL = 0.f, rawE = 0.f;
+      bool nvalid = grp < NS && grp * 64 + qcol < p.N;
+      if (nvalid) { rawL = lb[grp * 64 + qcol]; rawE = eb[grp * 64 + qcol]; }
+      auto chunk = [&](const uint32_t (&v)[16], const uint32_t (&g)[16], int col, int boff) {
         uint32_t pp[8], ds[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 Lq = L4[j >> 1], Eq = E4[j >> 1];
-          const float L0 = (j & 1) ? Lq.z : Lq.x, L1 = (j & 1) ? Lq.w : Lq.y;
-          const float E0 = (j & 1) ? Eq.z : Eq.x, E1 = (j & 1) ? Eq.w : Eq.y;
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -L0));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -L1));
-          pp[j] = pack_h2(p0, p1);
-          ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - E0), p1 * (__uint_as_float(g[2 * j + 1]) - E1));
+        for (int j = 0; j < 4; ++j) {        // four query columns per step: one broadcast 128-bit load of lse and of delta
+          const float4 L = reinterpret_cast<const float4*>(bc + boff)[j];
+          const float4 E = reinterpret_cast<const float4*>(bc + 32 + boff)[j];
+          float p0, p1, p2, p3;
+          ex2_pair(poly_slot<ATTN_BWD_POLY_PAIRS, 8>(2 * j), fmaf(__uint_as_float(v[4 * j]), c, -L.x), fmaf(__uint_as_float(v[4 * j + 1]), c, -L.y), p0, p1);
+          ex2_pair(poly_slot<ATTN_BWD_POLY_PAIRS, 8>(2 * j + 1), fmaf(__uint_as_float(v[4 * j + 2]), c, -L.z), fmaf(__uint_as_float(v[4 * j + 3]), c, -L.w), p2, p3);
+          pp[2 * j] = pack_h2(p0, p1);
+          pp[2 * j + 1] = pack_h2(p2, p3);
+          ds[2 * j] = pack_half2_sat(p0 * (__uint_as_float(g[4 * j]) - E.x), p1 * (__uint_as_float(g[4 * j + 1]) - E.y));
+          ds[2 * j + 1] = pack_half2_sat(p2 * (__uint_as_float(g[4 * j + 2]) - E.z), p3 * (__uint_as_float(g[4 * j + 3]) - E.w));
         }
         tmem_st_32x8(tmem_base + lane_off + col, pp);
         tmem_st_32x8(tmem_base + lane_off + kColDP + col, ds);
+      };
+      for (int i = grp; i < NS; i += 2) {
+        const uint32_t t = t_base + i;
+        const int s = t % kTB;
+        bc[lane] = nvalid ? rawL * kLog2eF : INFINITY;   // +inf -> P = 0 for padded queries
+        bc[32 + lane] = nvalid ? rawE : 0.f;
+        {
+          const int qi = (i + 2) * 64 + qcol;
+          nvalid = i + 2 < NS && qi < p.N;
+          if (nvalid) { rawL = lb[qi]; rawE = eb[qi]; }
+        }
+        if (warp == 2) TRACE(2, 120);
+        mbar_wait(&s_full[s], (t / kTB) & 1);
+        if (warp == 2) TRACE(2, 121);
+        tcgen05_fence_after();
+        __syncwarp();
+        const int col = s * 64 + half * 32;
+        uint32_t vA[16], gA[16], vB[16], gB[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, vA);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, gA);
+        tmem_ld_wait();
+        if (warp == 2) TRACE(2, 122);
+        tmem_ld_32x16(tmem_base + lane_off + col + 16, vB);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col + 16, gB);
+        chunk(vA, gA, col, 0);
+        tmem_ld_wait();
+        chunk(vB, gB, col + 16, 16);
+        if (warp == 2) TRACE(2, 123);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (warp == 2) TRACE(2, 124);
       }
+      t_it += NS;
       // item epilogue: dV lives in TMEM columns [384,448), dK in [448,512): warp `sub` takes columns 384 + sub*32
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
@@ -608,6 +723,7 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+  TRACE_DUMP();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -616,7 +732,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
                        const __grid_constant__ CUtensorMap tmOut16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  constexpr int NST = kBwdStages;
+  constexpr int NST = kDqStages;
   constexpr int kItem = 3 * kTile128;
   uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128 | O128] (O only feeds delta = rowsum(dO * O))
   uint8_t* St = smem + 2 * kItem;             // ring stage r at St + r * 2 * kTile64: [K64 | V64]
@@ -639,7 +755,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     tma_prefetch_desc(&tmQKV128); tma_prefetch_desc(&tmDO128); tma_prefetch_desc(&tmO128); tma_prefetch_desc(&tmQKV64);
     for (int s = 0; s < NST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kSoftmaxWarps); mbar_init(&sfree[s], 1); }
+    for (int s = 0; s < kTB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kPArrivals); mbar_init(&sfree[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kSoftmaxWarps);
     fence_barrier_init();
   }
@@ -694,8 +810,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         const int s = sd_it % kTB;
         const uint32_t ph = (sd_it / kTB) & 1;
         const int r = sd_it % NST;
-        mbar_wait(&kv_full[r], (sd_it / NST) & 1);
-        mbar_wait(&sfree[s], ph ^ 1);
+        mbar_wait2(&kv_full[r], (sd_it / NST) & 1, &sfree[s], ph ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kkd = desc_advance(kk0, r * 2 * kTile64);
@@ -724,8 +839,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         const uint32_t ph = (dq_it / kTB) & 1;
         const int r = dq_it % NST;
         if (i == 0) mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        mbar_wait(&kv_full[r], (dq_it / NST) & 1);
-        mbar_wait(&p_full[s], ph);
+        mbar_wait2(&kv_full[r], (dq_it / NST) & 1, &p_full[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kmd = desc_advance(km0, r * 2 * kTile64);
@@ -787,21 +901,15 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         dl = (xs[r] + xs[128 + r]) + (xs[256 + r] + xs[384 + r]);
         if (sub == 0 && row < p.N) p.delta_w[sidx] = dl;
       }
-      for (int i = 0; i < NS; ++i, ++t_it) {
-        const int s = t_it % kTB;
-        mbar_wait(&s_full[s], (t_it / kTB) & 1);
-        tcgen05_fence_after();
-        const int col = s * 64 + sub * 16;
-        const int kv_left = p.N - i * 64 - sub * 16;
-        uint32_t v[16], g[16];
-        tmem_ld_32x16(tmem_base + lane_off + col, v);
-        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, g);
-        tmem_ld_wait();
+      // two groups of eight warps on alternate key sub-tiles, 32 key columns per warp in two 16-column chunks (see the dKV kernel)
+      const int grp = sub & 1, half = sub >> 1;
+      const uint32_t t_base = item_it * (uint32_t)NS;
+      auto chunk = [&](const uint32_t (&v)[16], const uint32_t (&g)[16], int col, int kv_left) {
         uint32_t ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -lse2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2));
+          float p0, p1;
+          ex2_pair(poly_slot<ATTN_BWD_POLY_PAIRS, 8>(j), fmaf(__uint_as_float(v[2 * j]), c, -lse2), fmaf(__uint_as_float(v[2 * j + 1]), c, -lse2), p0, p1);
           ds[j] = pack_half2_sat(p0 * (__uint_as_float(g[2 * j]) - dl), p1 * (__uint_as_float(g[2 * j + 1]) - dl));
         }
         if (kv_left < 16) {                            // ragged last tile (warp-uniform): padded key columns contribute nothing
@@ -812,11 +920,29 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           }
         }
         tmem_st_32x8(tmem_base + lane_off + kColDP + col, ds);
+      };
+      for (int i = grp; i < NS; i += 2) {
+        const uint32_t t = t_base + i;
+        const int s = t % kTB;
+        mbar_wait(&s_full[s], (t / kTB) & 1);
+        tcgen05_fence_after();
+        const int col = s * 64 + half * 32;
+        const int kv_left = p.N - i * 64 - half * 32;
+        uint32_t vA[16], gA[16], vB[16], gB[16];
+        tmem_ld_32x16(tmem_base + lane_off + col, vA);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col, gA);
+        tmem_ld_wait();
+        tmem_ld_32x16(tmem_base + lane_off + col + 16, vB);
+        tmem_ld_32x16(tmem_base + lane_off + kColDP + col + 16, gB);
+        chunk(vA, gA, col, kv_left);
+        tmem_ld_wait();
+        chunk(vB, gB, col + 16, kv_left - 16);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
       }
+      t_it += NS;
       mbar_wait(acc_full, item_it & 1);
       tcgen05_fence_after();
       {
@@ -888,6 +1014,13 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   return 0;
 }
 
+#ifdef B200_ATTN16_TRACE
+extern "C" int b200vq_trace16_read(long long* out) {   // out[3][2 * 64]: (event, clock) pairs per role, zero padded
+  cudaMemcpyFromSymbol(out, g_trace16, sizeof(g_trace16));
+  return 0;
+}
+#endif
+
 // dout fp16 (carrying the gradient scale), out fp16; dqkv fp16 (same scale); delta scratch fp32 [B*heads*N]
 int attention_f16_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* delta, int B, int N,
                            int heads, int dh, float scale, cudaStream_t stream) {
@@ -912,8 +1045,9 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale;
-  constexpr int smem_kv = 4 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 128 + 1024;
-  constexpr int smem_q = 6 * kTile128 + kBwdStages * 2 * kTile64 + kBoxBytes + 512 + 1024 * 4 + 1024;
+  constexpr int smem_kv = 4 * kTile128 + kDkvStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 256 + 1024;
+  constexpr int smem_q = 6 * kTile128 + kDqStages * 2 * kTile64 + kBoxBytes + 512 + 1024 * 4 + 1024;
+  static_assert(smem_kv <= 227 * 1024 && smem_q <= 227 * 1024, "attention backward: shared-memory plan exceeds 227 KB");
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem_kv);
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem_q);
   const int grid = persistent_grid(p.total_items);

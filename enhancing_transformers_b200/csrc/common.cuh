@@ -195,6 +195,14 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b
   if (!da) mbar_wait(a, pa);
   if (!db) mbar_wait(b, pb);
 }
+__device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
+  const bool da = mbar_test(a, pa);
+  const bool db = mbar_test(b, pb);
+  const bool dc = mbar_test(c, pc);
+  if (!da) mbar_wait(a, pa);
+  if (!db) mbar_wait(b, pb);
+  if (!dc) mbar_wait(c, pc);
+}
 
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, completion on an mbarrier

@@ -491,6 +491,41 @@ def g_attn16():
     print(f"f16  bwd B={B}: {ms:.3f} ms {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
 
 
+def g_attn16_trace():
+    """timeline of the fp16 dKV kernel's two issuer warps and one softmax warp (needs B200VQ_LIB=.../libb200vq_trace16.so,
+    `make -C enhancing_transformers_b200/csrc trace16`)"""
+    import ctypes
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    L = ctypes.CDLL(etb._lib.LIB_PATH)
+    B, N, heads, dh = 32, 1024, 12, 64
+    inner = heads * dh
+    qkv = torch.randn(B * N, 3 * inner, device="cuda").half()
+    o, lse = ops.attention_f16_fwd(qkv, B, N, heads, dh, 0.125)
+    do = torch.randn(B * N, inner, device="cuda").half()
+    cap = 64
+    buf = (ctypes.c_longlong * (3 * 2 * cap))()
+    ops.attention_f16_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125)
+    torch.cuda.synchronize()
+    L.b200vq_trace16_read(buf)
+    ev = []
+    for r in range(3):
+        for i in range(cap):
+            e, t = buf[r * 2 * cap + 2 * i], buf[r * 2 * cap + 2 * i + 1]
+            if t:
+                ev.append((t, r, e))
+    ev.sort()
+    names = {100: "A: wait qd_full", 101: "A: got qd_full, wait sfree", 102: "A: got sfree", 103: "A: issued S^T, dP^T",
+             110: "B: got qd_full, wait p_full", 111: "B: got p_full", 112: "B: issued dV, dK",
+             120: "sm: wait s_full", 121: "sm: got s_full", 122: "sm: tcgen05.ld done", 123: "sm: computed", 124: "sm: stored + arrived"}
+    t0 = ev[0][0] if ev else 0
+    prev = t0
+    for t, r, e in ev:
+        print(f"{t - t0:9d} (+{t - prev:5d})  {names.get(e, e)}")
+        prev = t
+
+
 def g_attn_trace():
     """timeline of the dQ kernel's MMA warp and two softmax warps (needs B200VQ_LIB=.../libb200vq_trace.so)"""
     import ctypes
