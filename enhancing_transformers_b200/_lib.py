@@ -28,7 +28,7 @@ _SIGNATURES = {
     "b200vq_splitk_reduce": (c_i, [c_f, c_i, c_ll, c_ll, c_f, c_f, c_f]),
     "b200vq_layernorm_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f]),
     "b200vq_layernorm_bwd_workspace_bytes": (c_sz, [c_i]),
-    "b200vq_layernorm_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
+    "b200vq_layernorm_bwd": (c_i, [c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_sz, c_f]),
     "b200vq_attention_fwd": (c_i, [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "b200vq_attention_bwd": (c_i, [c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "b200vq_attention_f16_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f]),

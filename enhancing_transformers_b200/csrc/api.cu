@@ -66,7 +66,7 @@ int gemm_f16(const void*, long long, int, const void*, long long, int, void*, lo
 int splitk_reduce(const float*, int, long long, long long, const float*, float*, cudaStream_t);
 int layernorm_forward(const float*, const float*, const float*, float*, void*, float*, float*, int, int, int, cudaStream_t);
 size_t layernorm_bwd_workspace_bytes(int);
-int layernorm_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*, void*,
+int layernorm_backward(const void*, int, const float*, const float*, const float*, const float*, const float*, const float*, float*, void*,
                        const float*, float*, float*, float*, int, int, int, void*, size_t, cudaStream_t);
 int attention_forward(const float*, void*, int, float*, int, int, int, int, float, int, cudaStream_t);
 int attention_backward(const float*, const void*, int, const float*, const float*, void*, int, const float*, float*, int, int,
@@ -138,10 +138,10 @@ int b200vq_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
   return layernorm_forward(x, gamma, beta, y, y16, mean, rstd, M, D, round_out, S(stream));
 }
 size_t b200vq_layernorm_bwd_workspace_bytes(int D) { return layernorm_bwd_workspace_bytes(D); }
-int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, void* dx16, const float* dx16_scale, float* dgamma, float* dbeta,
-                         float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes, void* stream) {
-  return layernorm_backward(dy, x, mean, rstd, gamma, dres, dx, dx16, dx16_scale, dgamma, dbeta, dxsum, M, D, round_out,
+int b200vq_layernorm_bwd(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, const float* dres, float* dx, void* dx16, const float* dx16_scale, float* dgamma,
+                         float* dbeta, float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes, void* stream) {
+  return layernorm_backward(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, dx16_scale, dgamma, dbeta, dxsum, M, D, round_out,
                             workspace, ws_bytes, S(stream));
 }
 int b200vq_attention_fwd(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, int dh, float scale,

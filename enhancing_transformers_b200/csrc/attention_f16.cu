@@ -248,6 +248,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   float* xch = reinterpret_cast<float*>(k_full + 4 * NST + 2);   // [2][4][128] row-max (double buffered) + [4][128] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
@@ -314,7 +315,9 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int s = s_it & 1;                       // TMEM S buffer
         const uint32_t ph = (s_it >> 1) & 1;
         const int r = s_it % NST;                     // K ring stage
+        TRACE(0, 200);
         mbar_wait2(&k_full[r], (s_it / NST) & 1, &sfree[s], ph ^ 1);
+        TRACE(0, 201);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t kd = desc_advance(kd0, r * kTile128);
@@ -326,6 +329,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           if (j == T - 1) umma_commit<1>(&q_empty[qs]);
         }
         __syncwarp();
+        TRACE(0, 202);
       }
     }
   } else if (warp == kIssuerB) {
@@ -338,7 +342,9 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int s = pv_it & 1;
         const uint32_t ph = (pv_it >> 1) & 1;
         const int r = pv_it % NST;                    // V ring stage
+        TRACE(1, 210);
         mbar_wait3(&v_full[r], (pv_it / NST) & 1, &o_empty[s], ph ^ 1, &p_full[s], ph);
+        TRACE(1, 211);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t vd = desc_advance(vd0, r * kTile128);
@@ -350,6 +356,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           umma_commit<1>(&sfree[s]);
         }
         __syncwarp();
+        TRACE(1, 212);
       }
     }
   } else {
@@ -395,6 +402,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           for (int i = 0; i < 32; ++i)
             if (i >= kv_left) v0[i] = 0xff800000u;          // -inf
         }
+        if (warp == 2) TRACE(2, 220);
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v0[i]));
@@ -402,6 +410,7 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         xs[sub * 128 + row_in_tile] = mx;
         quad_bar(q);        // also orders the partners' S loads before this thread's packed P stores (they overlap their columns)
         mx = fmaxf(fmaxf(xs[row_in_tile], xs[128 + row_in_tile]), fmaxf(xs[256 + row_in_tile], xs[384 + row_in_tile]));
+        if (warp == 2) TRACE(2, 221);
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
@@ -415,11 +424,13 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           pk[i] = pack_h2(a0, a1);
         }
         sum += sum1;
+        if (warp == 2) TRACE(2, 222);
         tmem_st_32x16(tmem_base + lane_off + s * 128 + sub * 16, pk);     // P columns [0,64) of the S buffer
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
+        if (warp == 2) TRACE(2, 223);
         l = fmaf(l, alpha, sum);
         const bool more = j + 1 < T;
         const uint32_t ph_s = ((t_it + 1) >> 1) & 1, ph_o = ((t_it - 1) >> 1) & 1;
@@ -427,9 +438,11 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         else if (more)      mbar_wait(&s_full[s ^ 1], ph_s);
         else if (j >= 1)    mbar_wait(&o_full[s ^ 1], ph_o);
         tcgen05_fence_after();
+        if (warp == 2) TRACE(2, 224);
         if (more) tmem_ld_32x32(tmem_base + lane_off + (s ^ 1) * 128 + sub * 32, v0);
         if (j >= 1) fold_pv(t_it - 1, alpha_prev);
         else        tmem_ld_wait();
+        if (warp == 2) TRACE(2, 225);
         alpha_prev = alpha;
         m = m_new;
       }
@@ -453,6 +466,9 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+#ifdef B200_ATTN16_TRACE_FWD
+  TRACE_DUMP();
+#endif
 }
 
 // =============================================================================================
@@ -723,7 +739,9 @@ attn_bwd_dkv_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+#ifndef B200_ATTN16_TRACE_FWD
   TRACE_DUMP();
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads, 1)

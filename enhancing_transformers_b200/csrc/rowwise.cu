@@ -79,14 +79,19 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // shared-memory slab (conflict-free float4 read-modify-write per row), which leaves the register file to
 // the row being loaded, and the dres row is requested together with x and dy so a row costs one HBM
 // round trip, not two.
-template <int NV, int NACC>
+// DYH: dy arrives as fp16 carrying a gradient scale (the output of an fp16 dgrad GEMM) and is multiplied by *dy_scale (1/S)
+// on the way in: the GEMM writes, and this kernel reads, half the bytes of the fp32 hand-off.
+template <int NV, int NACC, int DYH>
 __global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
-              float* __restrict__ dx, __half* __restrict__ dx16, const float* __restrict__ scale_ptr,
-              float* __restrict__ part, int M, int D, int round_out) {
+ln_bwd_kernel(const void* __restrict__ dyv, const float* __restrict__ dy_scale, const float* __restrict__ x,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              const float* __restrict__ dres, float* __restrict__ dx, __half* __restrict__ dx16,
+              const float* __restrict__ scale_ptr, float* __restrict__ part, int M, int D, int round_out) {
   extern __shared__ float sm[];   // [warps][NACC][D]
   const float gscale = (dx16 && scale_ptr) ? __ldg(scale_ptr) : 1.f;   // gradient scale of the fp16 copy
+  const float dys = (DYH && dy_scale) ? __ldg(dy_scale) : 1.f;
+  const float* dy = static_cast<const float*>(dyv);
+  const __half* dyh = static_cast<const __half*>(dyv);
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 2;
@@ -105,6 +110,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
     const float4* gr = reinterpret_cast<const float4*>(dy + (size_t)row * D);
+    const uint2* gh = reinterpret_cast<const uint2*>(dyh + (size_t)row * D);
     const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * D) : nullptr;
     float4 xh[NV], g[NV], r[NV];
 #pragma unroll
@@ -113,7 +119,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       xh[i] = zero4; g[i] = zero4; r[i] = zero4;
       if (c < nv) {
         xh[i] = xr[c];
-        g[i] = gr[c];
+        if (DYH) {
+          const uint2 pk = gh[c];
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+          g[i] = make_float4(lo.x * dys, lo.y * dys, hi.x * dys, hi.y * dys);
+        } else {
+          g[i] = gr[c];
+        }
         if (rr) r[i] = rr[c];
       }
     }
@@ -438,30 +451,30 @@ int layernorm_bwd_blocks() { return num_sms() * 2; }
 size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)layernorm_bwd_blocks() * 3 * D * sizeof(float); }
 
 template <int NV, int NACC>
-static int ln_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+static int ln_bwd_launch(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* dres, float* dx, __half* dx16, const float* scale_ptr, float* part, int M, int D, int round_out,
                          int blocks, cudaStream_t s) {
   const size_t smem = (size_t)8 * NACC * D * sizeof(float);
-  auto kern = ln_bwd_kernel<NV, NACC>;
+  auto kern = dy_half ? ln_bwd_kernel<NV, NACC, 1> : ln_bwd_kernel<NV, NACC, 0>;
   if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, 256, smem, s>>>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out);
+  kern<<<blocks, 256, smem, s>>>(dy, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out);
   return 0;
 }
 
 template <int NACC>
-static int ln_bwd_dispatch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+static int ln_bwd_dispatch(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean, const float* rstd, const float* gamma,
                            const float* dres, float* dx, __half* dx16, const float* scale_ptr, float* part, int M, int D,
                            int round_out, int blocks, cudaStream_t s) {
   const int nv = (D + 127) / 128;
-  if (nv <= 1) return ln_bwd_launch<1, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
-  if (nv <= 2) return ln_bwd_launch<2, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
-  if (nv <= 4) return ln_bwd_launch<4, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
-  if (nv <= 6) return ln_bwd_launch<6, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
-  if (nv <= 10) return ln_bwd_launch<10, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
-  return ln_bwd_launch<16, NACC>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 1) return ln_bwd_launch<1, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 2) return ln_bwd_launch<2, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 4) return ln_bwd_launch<4, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 6) return ln_bwd_launch<6, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  if (nv <= 10) return ln_bwd_launch<10, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
+  return ln_bwd_launch<16, NACC>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, s);
 }
 
-int layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+int layernorm_backward(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean, const float* rstd, const float* gamma,
                        const float* dres, float* dx, void* dx16v, const float* scale_ptr, float* dgamma, float* dbeta,
                        float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   __half* dx16 = static_cast<__half*>(dx16v);
@@ -471,8 +484,8 @@ int layernorm_backward(const float* dy, const float* x, const float* mean, const
   if (blocks > (M + 7) / 8) blocks = (M + 7) / 8;
   float* part = static_cast<float*>(workspace);
   const int nacc = dxsum ? 3 : 2;
-  int rc = dxsum ? ln_bwd_dispatch<3>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream)
-                 : ln_bwd_dispatch<2>(dy, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream);
+  int rc = dxsum ? ln_bwd_dispatch<3>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream)
+                 : ln_bwd_dispatch<2>(dy, dy_half, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out, blocks, stream);
   if (rc) return rc;
   B200_LAUNCH_OK("ln_bwd_kernel");
   ln_param_reduce_kernel<<<(nacc * D + 31) / 32, 256, 0, stream>>>(part, blocks, D, nacc, dgamma, dbeta, dxsum);

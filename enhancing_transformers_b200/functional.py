@@ -292,9 +292,9 @@ def _block_bwd_f16(saved, prm, dims, g, g_colsum, gh, sc, need_w):
     else:
         dt = ops.gemm(gh, w2h, M, mlp, D, b_major=1, aux=t, out_half=True, cta_group=cg)
     dw1 = _wgrad(dt, h2, mlp, D, inv_scale=inv) if need_w else None
-    dh2 = ops.gemm(dt, w1h, M, D, mlp, b_major=1, alpha=inv, cta_group=cg)
+    dh2 = ops.gemm(dt, w1h, M, D, mlp, b_major=1, out_half=True, cta_group=cg)                      # fp16, carries S
     del dt
-    g1, dln2_w, dln2_b, dbo, g1h = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2_w, g, want_colsum=True, half_scale=S)
+    g1, dln2_w, dln2_b, dbo, g1h = ops.layernorm_bwd(dh2, x1, mean2, rstd2, ln2_w, g, want_colsum=True, half_scale=S, dy_scale=inv)
     del dh2
     # ---- attention branch
     dwo = _wgrad(g1h, o, D, inner, inv_scale=inv) if need_w else None
@@ -306,9 +306,9 @@ def _block_bwd_f16(saved, prm, dims, g, g_colsum, gh, sc, need_w):
         dqkv = ops.attention_bwd(qkv, o, lse, do, B, N, heads, dh, scale, False, half_scale=S)     # fp16, carries S
     del g1h, do
     dwq = _wgrad(dqkv, h1, 3 * inner, D, inv_scale=inv) if need_w else None
-    dh1 = ops.gemm(dqkv, wq, M, D, 3 * inner, b_major=1, alpha=inv, cta_group=cg)
+    dh1 = ops.gemm(dqkv, wq, M, D, 3 * inner, b_major=1, out_half=True, cta_group=cg)               # fp16, carries S
     del dqkv
-    gx, dln1_w, dln1_b, gx_sum, gxh = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, g1, want_colsum=True, half_scale=S)
+    gx, dln1_w, dln1_b, gx_sum, gxh = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, g1, want_colsum=True, half_scale=S, dy_scale=inv)
     grads = (dln1_w, dln1_b, dwq, dwo, dbo, dln2_w, dln2_b, dw1, db1, dw2, db2) if need_w else (None,) * LAYER_PARAMS
     return gx, gx_sum, gxh, grads
 

@@ -183,10 +183,14 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, round_out: bool, out_h
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dres: Optional[Tensor],
-                  round_out: bool = False, want_colsum: bool = False, half_scale: Optional[Tensor] = None):
+                  round_out: bool = False, want_colsum: bool = False, half_scale: Optional[Tensor] = None,
+                  dy_scale: Optional[Tensor] = None):
     """-> (dx, dgamma, dbeta) or, with want_colsum, (dx, dgamma, dbeta, colsum(dx)); with half_scale (device
-    scalar) a further element: the fp16 copy fp16(dx * scale)"""
-    _req(dy, "dy"); _req(x, "x"); _req(dres, "dres"); _req(half_scale, "half_scale")
+    scalar) a further element: the fp16 copy fp16(dx * scale).  dy may be fp16 (the scaled output of an fp16 dgrad
+    GEMM): it is multiplied by the device scalar dy_scale (1/S) as it is read."""
+    dy_half = dy.dtype == _HALF
+    _req(dy, "dy", _HALF if dy_half else torch.float32); _req(x, "x"); _req(dres, "dres"); _req(half_scale, "half_scale")
+    _req(dy_scale, "dy_scale")
     D = x.shape[-1]
     M = x.numel() // D
     L = _lib.lib()
@@ -197,7 +201,7 @@ def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tens
     dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
     dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
     dxsum = torch.empty(D, device=x.device, dtype=torch.float32) if want_colsum else None
-    _lib.check(L.b200vq_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(half_scale),
+    _lib.check(L.b200vq_layernorm_bwd(_p(dy), int(dy_half), _p(dy_scale), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(half_scale),
                                       _p(dgamma), _p(dbeta), _p(dxsum), M, D, int(round_out), _p(ws), ws_bytes, _stream()),
                "layernorm_bwd")
     res = (dx, dgamma, dbeta) + ((dxsum,) if want_colsum else ())

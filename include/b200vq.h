@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200VQ_VERSION 200 /* 0.2.0 */
+#define B200VQ_VERSION 201 /* 0.2.1 */
 
 int b200vq_version(void);
 const char* b200vq_last_error(void);
@@ -91,11 +91,13 @@ size_t b200vq_layernorm_bwd_workspace_bytes(int D);
 /* dx = LN'(dy) (+ dres, the skip-connection gradient of layers.py:147-148).  dxsum (nullable, [D]) receives the
  * column sums of dx: dx is also the gradient at the bias of the Linear that wrote this residual stream
  * (to_out layers.py:118, net.2 layers.py:101), so that bias gradient costs no extra pass over dx.
- * dx16 (nullable): fp16 copy of dx multiplied by *dx16_scale, the operand of the next block's fp16 GEMMs. */
-int b200vq_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* dres, float* dx, void* dx16, const float* dx16_scale, float* dgamma,
-                         float* dbeta, float* dxsum, int M, int D, int round_out, void* workspace, size_t ws_bytes,
-                         void* stream);
+ * dx16 (nullable): fp16 copy of dx multiplied by *dx16_scale, the operand of the next block's fp16 GEMMs.
+ * dy: fp32, or (dy_half = 1) fp16 carrying a gradient scale -- the fp16 output of a dgrad GEMM -- multiplied by
+ * *dy_scale (device scalar 1/S, or NULL) as it is read. */
+int b200vq_layernorm_bwd(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean,
+                         const float* rstd, const float* gamma, const float* dres, float* dx, void* dx16,
+                         const float* dx16_scale, float* dgamma, float* dbeta, float* dxsum, int M, int D, int round_out,
+                         void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- attention core (layers.py:124-130): softmax(q k^T * scale) v, no mask -----------------------
  * qkv is the [B*N, 3*heads*dh] output of to_qkv (q | k | v thirds, head h at columns h*dh);

@@ -162,6 +162,13 @@ def test_layernorm_fp16_outputs(M, D):
     dx2, dg2, db2, dxs2, dxh = ops.layernorm_bwd(dy, x, mean, rstd, g, dres, want_colsum=True, half_scale=sc[0:1])
     assert torch.equal(dx, dx2) and torch.equal(dg, dg2)
     assert torch.equal(dxh, (dx * sc[0]).to(H))
+    # fp16 dy carrying the gradient scale (what an fp16 dgrad GEMM hands over): the kernel multiplies by 1/S as it reads,
+    # so the result is bit-identical to the fp32 path fed with the same (fp16-representable) values
+    dyh = ops.to_half(dy, sc[0:1])
+    dy_rt = dyh.float() * sc[1]
+    dx3, dg3, db3, dxs3 = ops.layernorm_bwd(dy_rt, x, mean, rstd, g, dres, want_colsum=True)
+    dx4, dg4, db4, dxs4 = ops.layernorm_bwd(dyh, x, mean, rstd, g, dres, want_colsum=True, dy_scale=sc[1:2])
+    assert torch.equal(dx3, dx4) and torch.equal(dg3, dg4) and torch.equal(db3, db4) and torch.equal(dxs3, dxs4)
 
 
 def test_grad_scale_and_to_half():

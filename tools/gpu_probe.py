@@ -507,6 +507,8 @@ def g_attn16_trace():
     cap = 64
     buf = (ctypes.c_longlong * (3 * 2 * cap))()
     ops.attention_f16_bwd(qkv, o, lse, do, B, N, heads, dh, 0.125)
+    if os.environ.get("TRACE_FWD"):      # a library built with -DB200_ATTN16_TRACE_FWD dumps the forward kernel's timeline instead
+        ops.attention_f16_fwd(qkv, B, N, heads, dh, 0.125)
     torch.cuda.synchronize()
     L.b200vq_trace16_read(buf)
     ev = []
@@ -518,7 +520,10 @@ def g_attn16_trace():
     ev.sort()
     names = {100: "A: wait qd_full", 101: "A: got qd_full, wait sfree", 102: "A: got sfree", 103: "A: issued S^T, dP^T",
              110: "B: got qd_full, wait p_full", 111: "B: got p_full", 112: "B: issued dV, dK",
-             120: "sm: wait s_full", 121: "sm: got s_full", 122: "sm: tcgen05.ld done", 123: "sm: computed", 124: "sm: stored + arrived"}
+             120: "sm: wait s_full", 121: "sm: got s_full", 122: "sm: tcgen05.ld done", 123: "sm: computed", 124: "sm: stored + arrived",
+             200: "A: wait k_full+sfree", 201: "A: got them", 202: "A: issued S", 210: "B: wait v_full+o_empty+p_full", 211: "B: got them",
+             212: "B: issued PV", 220: "sm: S in registers", 221: "sm: row max exchanged", 222: "sm: exps done", 223: "sm: P stored + arrived",
+             224: "sm: got next S / prev PV", 225: "sm: PV folded"}
     t0 = ev[0][0] if ev else 0
     prev = t0
     for t, r, e in ev:
