@@ -12,10 +12,10 @@ from .functional import get_precision, invalidate_shadows, set_precision  # noqa
 from .layers import (Attention, FeedForward, PreNorm, QuantLinear, Transformer, ViTDecoder, ViTEncoder,  # noqa: F401
                      sincos_table)
 from .parallel import FlatGradients, allreduce_gradients  # noqa: F401
-from .quantizers import BaseQuantizer, VectorQuantizer  # noqa: F401
+from .quantizers import BaseQuantizer, GumbelQuantizer, VectorQuantizer  # noqa: F401
 
 __version__ = "0.2.0"
-__all__ = ["ViTEncoder", "ViTDecoder", "VectorQuantizer", "BaseQuantizer", "Transformer", "Attention", "FeedForward",
+__all__ = ["ViTEncoder", "ViTDecoder", "VectorQuantizer", "GumbelQuantizer", "BaseQuantizer", "Transformer", "Attention", "FeedForward",
            "PreNorm", "QuantLinear", "patch", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
            "get_precision", "invalidate_shadows", "allreduce_gradients", "FlatGradients", "ops", "functional", "configs"]
 
@@ -32,6 +32,7 @@ def patch(vitvqgan_module=None):
     vitvqgan_module.Encoder = ViTEncoder
     vitvqgan_module.Decoder = ViTDecoder
     vitvqgan_module.VectorQuantizer = VectorQuantizer
+    vitvqgan_module.GumbelQuantizer = GumbelQuantizer      # ViTVQGumbel (vitvqgan.py:147-176)
     _wrap_vitvq_init(vitvqgan_module)
     return vitvqgan_module
 
@@ -78,10 +79,7 @@ def install_as_reference_modules():
     qua.VectorQuantizer = _quantizers.VectorQuantizer
     qua.BaseQuantizer = _quantizers.BaseQuantizer
 
-    class _GumbelUnavailable:  # vitvqgan.py:21 imports the name; ViTVQGumbel is out of scope
-        def __init__(self, *a, **k):
-            raise NotImplementedError("GumbelQuantizer is not part of the B200 hot path; use the reference class")
-    qua.GumbelQuantizer = _GumbelUnavailable
+    qua.GumbelQuantizer = _quantizers.GumbelQuantizer
     sys.modules[lay.__name__] = lay
     sys.modules[qua.__name__] = qua
     return lay, qua

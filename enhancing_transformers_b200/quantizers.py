@@ -11,6 +11,8 @@ Forward and backward each run as one fused CUDA launch sequence (csrc/vq.cu); th
 [tokens, n_embed] distance matrix of quantizers.py:78-80 is never materialised."""
 from __future__ import annotations
 
+import math
+from functools import partial
 from typing import Optional, Tuple
 
 import torch
@@ -70,3 +72,51 @@ class VectorQuantizer(BaseQuantizer):
         lead = code.shape[:-1] if self.use_residual else code.shape
         return ops.vq_embed(self.embedding.weight.detach(), code.contiguous().view(-1, depth), depth,
                             bool(self.use_norm)).view(*lead, self.embed_dim)
+
+
+class GumbelQuantizer(BaseQuantizer):
+    """Drop-in for the reference's ``GumbelQuantizer`` (quantizers.py:95-126; used by ``ViTVQGumbel``, vitvqgan.py:147-176).
+
+    Same constructor and the same ``(z_q, kl-to-uniform loss, indices)`` triple.  The two contractions -- the
+    [tokens, n_embed] logit matrix ``-|z|^2 - |e|^2 + 2 z e^T`` and ``soft_one_hot @ codebook`` -- run on the tcgen05 GEMM
+    (3xTF32: the logits feed a softmax with temperature, so they keep fp32-grade accuracy); the Gumbel noise, the softmax
+    and the KL term are PyTorch (``F.gumbel_softmax`` draws from the same generator as the reference, so a seeded run
+    reproduces the reference's samples up to the rounding of the logits).  Unlike the arg-min lookup this quantiser is
+    stochastic -- in eval mode too (hard one-hot of a noisy arg-max) -- so parity with the reference is distributional,
+    not bit-wise (tests/test_gpu_model.py::test_gumbel_quantizer_matches_reference)."""
+
+    def __init__(self, embed_dim: int, n_embed: int, temp_init: float = 1.0, use_norm: bool = True,
+                 use_residual: bool = False, num_quantizers: Optional[int] = None, **kwargs) -> None:
+        super().__init__(embed_dim, n_embed, False, use_norm, use_residual, num_quantizers)
+        self.temperature = temp_init
+
+    def quantize(self, z: torch.Tensor, temp: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        hard = not self.training            # the reference forces a hard sample in eval mode (quantizers.py:105-106)
+        temp = self.temperature if temp is None else temp
+        zn = self.norm(z.reshape(-1, self.embed_dim)).contiguous()
+        en = self.norm(self.embedding.weight).contiguous()
+        dots = Fn.LinearFn.apply(zn, en, None, 0, True)                                   # [tokens, n_embed]
+        logits = 2.0 * dots - zn.pow(2).sum(dim=1, keepdim=True) - en.pow(2).sum(dim=1)
+        logits = logits.view(*z.shape[:-1], -1)
+        soft_one_hot = F.gumbel_softmax(logits, tau=temp, dim=-1, hard=hard)
+        z_q = Fn.LinearFn.apply(soft_one_hot.reshape(-1, self.n_embed).contiguous(), en.t().contiguous(), None, 0, True)
+        z_q = z_q.view(*z.shape[:-1], self.embed_dim)
+        logp = F.log_softmax(logits, dim=-1)
+        loss = torch.sum(logp.exp() * (logp + math.log(self.n_embed)), dim=-1).mean()
+        return z_q, loss, soft_one_hot.argmax(dim=-1)
+
+    def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """quantizers.py:38-63 with straight_through = False: z_q carries the gradient of the soft sample"""
+        if not self.use_residual:
+            return self.quantize(z)
+        z_q = torch.zeros_like(z)
+        residual = z.detach().clone()
+        losses, codes = [], []
+        for _ in range(int(self.num_quantizers)):
+            z_qi, loss, idx = self.quantize(residual.clone())
+            residual = residual - z_qi          # like the reference's in-place sub_: later stages back-propagate into earlier samples
+            z_q = z_q + z_qi
+            codes.append(idx)
+            losses.append(loss)
+        losses, codes = map(partial(torch.stack, dim=-1), (losses, codes))
+        return z_q, losses.mean(), codes

@@ -454,3 +454,54 @@ def test_non_square_patches_match_the_reference_modules():
     assert relmax(dec(h).cpu(), rec_ref.detach()) < 5e-5
     with pytest.raises(NotImplementedError, match="multiple of 4"):
         etb.ViTEncoder(image_size=30, patch_size=6, dim=64, depth=1, heads=2, mlp_dim=64)
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_gumbel_quantizer_matches_reference(residual):
+    """reference quantizers.py:95-126.  The quantiser is stochastic; with the generator seeded
+    identically F.gumbel_softmax draws the same noise on the same device, so the soft sample, the KL loss and the
+    gradients of the vendored reference class (oracle/_ref, moved to the GPU, TF32 matmuls off) are reproduced up to
+    the rounding of the logits; in eval mode (hard one-hot of a noisy arg-max) the indices agree except at near-ties."""
+    import importlib.util
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "enhancing_ref")
+    if not os.path.exists(os.path.join(ref_dir, "quantizers.py")):
+        pytest.skip("oracle/_ref not present")
+    spec = importlib.util.spec_from_file_location("enhancing_ref_ns.quantizers", os.path.join(ref_dir, "quantizers.py"))
+    RQ = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RQ)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    kw = dict(embed_dim=32, n_embed=512, temp_init=0.7, use_residual=residual, num_quantizers=3 if residual else None)
+    torch.manual_seed(0)
+    ref = RQ.GumbelQuantizer(**kw).cuda()
+    ours = etb.GumbelQuantizer(**kw).cuda()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    z0 = torch.randn(2, 96, 32, device="cuda")
+    # training mode: soft samples, gradients through the sample
+    outs = []
+    for q in (ref, ours):
+        q.train(); q.zero_grad()
+        z = z0.clone().requires_grad_(True)
+        torch.manual_seed(123)
+        zq, loss, idx = q(z)
+        (zq.square().mean() + loss).backward()
+        outs.append((zq.detach(), loss.detach(), idx, z.grad, q.embedding.weight.grad.clone()))
+    (zq_r, l_r, i_r, gz_r, ge_r), (zq_o, l_o, i_o, gz_o, ge_o) = outs
+    assert zq_o.shape == zq_r.shape and i_o.shape == i_r.shape and i_o.dtype == torch.int64
+    assert relmax(zq_o, zq_r) < 2e-4 and abs(float(l_o - l_r)) < 1e-5 * max(1.0, abs(float(l_r)))
+    assert (i_o == i_r).float().mean() > 0.99
+    if gz_r is None:          # residual mode quantises a detached copy of z (quantizers.py:43) and has no straight-through term
+        assert gz_o is None
+    else:
+        assert relmax(gz_o, gz_r) < 2e-3
+    assert relmax(ge_o, ge_r) < 2e-3
+    # eval mode: hard samples
+    with torch.no_grad():
+        res = []
+        for q in (ref, ours):
+            q.eval()
+            torch.manual_seed(7)
+            res.append(q(z0))
+    assert (res[0][2] == res[1][2]).float().mean() > 0.99
+    same = (res[0][2] == res[1][2])
+    same = same.all(-1) if residual else same
+    assert relmax(res[1][0][same], res[0][0][same]) < 1e-4
