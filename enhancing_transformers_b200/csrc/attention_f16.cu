@@ -41,7 +41,7 @@ constexpr int kFwdStages = 4;      // K and V rings of the forward kernel (128-r
 #define ATTN_DKV_STAGES 6
 #endif
 #ifndef ATTN_DQ_STAGES
-#define ATTN_DQ_STAGES 5           // the dQ kernel keeps three 128-row item tiles per buffer: one stage fewer fits
+#define ATTN_DQ_STAGES 6
 #endif
 constexpr int kDkvStages = ATTN_DKV_STAGES;
 constexpr int kDqStages = ATTN_DQ_STAGES;
@@ -755,7 +755,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   uint8_t* QDs = smem;                        // [2] item buffers [Q128 | dO128 | O128] (O only feeds delta = rowsum(dO * O))
   uint8_t* St = smem + 2 * kItem;             // ring stage r at St + r * 2 * kTile64: [K64 | V64]
   uint8_t* obox = St + NST * 2 * kTile64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes / 2);   // 32-row x 32-byte boxes: 1 KB per softmax warp
   uint64_t* q_full = bars + 0;     // [2]
   uint64_t* q_empty = bars + 2;    // [2]
   uint64_t* acc_full = bars + 4;
@@ -970,7 +970,7 @@ attn_bwd_dq_f16_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         float r[OC];
 #pragma unroll
         for (int j = 0; j < OC; ++j) r[j] = __uint_as_float(v[j]);
-        store_box_h16(obox + (warp - 2) * 2048, &tmOut16, r, p.scale, h * DH + sub * OC, qt * 128 + q * 32, b, lane);
+        store_box_h16(obox + (warp - 2) * 1024, &tmOut16, r, p.scale, h * DH + sub * OC, qt * 128 + q * 32, b, lane);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1064,7 +1064,7 @@ int attention_f16_backward(const void* qkv, const void* out, const float* lse, c
   p.total_items = p.tiles128 * heads * B;
   p.scale = scale;
   constexpr int smem_kv = 4 * kTile128 + kDkvStages * 2 * kTile64 + kBoxBytes + 512 + kSoftmaxWarps * 256 + 1024;
-  constexpr int smem_q = 6 * kTile128 + kDqStages * 2 * kTile64 + kBoxBytes + 512 + 1024 * 4 + 1024;
+  constexpr int smem_q = 6 * kTile128 + kDqStages * 2 * kTile64 + kBoxBytes / 2 + 512 + 1024 * 4 + 1024;
   static_assert(smem_kv <= 227 * 1024 && smem_q <= 227 * 1024, "attention backward: shared-memory plan exceeds 227 KB");
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dkv_f16_kernel, smem_kv);
   B200_CONFIGURE_SMEM_ONCE(attn_bwd_dq_f16_kernel, smem_q);

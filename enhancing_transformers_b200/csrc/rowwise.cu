@@ -98,6 +98,12 @@ ln_bwd_kernel(const void* __restrict__ dyv, const float* __restrict__ dy_scale, 
   float4* acc_g = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D);
   float4* acc_b = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D + D);
   float4* acc_o = reinterpret_cast<float4*>(sm + (size_t)warp * NACC * D + 2 * D);   // used when NACC == 3
+  // fp16 dy: a lane's four columns are 8 bytes, and 8-byte loads halve the bytes each load instruction keeps in flight
+  // (measured: the fp16 row read was SLOWER than the fp32 one, 296 vs 272 us).  With D % 8 == 0 the warp therefore fetches the
+  // row as 16-byte loads (lane l: halfs 8l..8l+7 of each 256-column block), parks it in a private shared-memory slab and
+  // every lane picks up its own 8 bytes per chunk from there.
+  const bool wide16 = DYH && (D & 7) == 0;
+  uint4* stage = reinterpret_cast<uint4*>(sm + (size_t)warps_per_block * NACC * D) + (size_t)warp * (D >> 3);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -113,21 +119,45 @@ ln_bwd_kernel(const void* __restrict__ dyv, const float* __restrict__ dy_scale, 
     const uint2* gh = reinterpret_cast<const uint2*>(dyh + (size_t)row * D);
     const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * D) : nullptr;
     float4 xh[NV], g[NV], r[NV];
+    constexpr int NV16 = (NV + 1) / 2;
+    uint4 wide[NV16];
+    if (wide16) {
+#pragma unroll
+      for (int i = 0; i < NV16; ++i) {
+        const int c = lane + i * 32;
+        if (c < (D >> 3)) wide[i] = reinterpret_cast<const uint4*>(gh)[c];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {          // all of the row's HBM requests go out back to back
       const int c = lane + i * 32;
-      xh[i] = zero4; g[i] = zero4; r[i] = zero4;
+      xh[i] = zero4; r[i] = zero4;
       if (c < nv) {
         xh[i] = xr[c];
+        if (rr) r[i] = rr[c];
+      }
+    }
+    if (wide16) {
+#pragma unroll
+      for (int i = 0; i < NV16; ++i) {
+        const int c = lane + i * 32;
+        if (c < (D >> 3)) stage[c] = wide[i];
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      g[i] = zero4;
+      if (c < nv) {
         if (DYH) {
-          const uint2 pk = gh[c];
+          const uint2 pk = wide16 ? reinterpret_cast<const uint2*>(stage)[c] : gh[c];
           const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
           const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
           g[i] = make_float4(lo.x * dys, lo.y * dys, hi.x * dys, hi.y * dys);
         } else {
           g[i] = gr[c];
         }
-        if (rr) r[i] = rr[c];
       }
     }
     const float mu = mean[row], rs = rstd[row];
@@ -454,7 +484,7 @@ template <int NV, int NACC>
 static int ln_bwd_launch(const void* dy, int dy_half, const float* dy_scale, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* dres, float* dx, __half* dx16, const float* scale_ptr, float* part, int M, int D, int round_out,
                          int blocks, cudaStream_t s) {
-  const size_t smem = (size_t)8 * NACC * D * sizeof(float);
+  const size_t smem = (size_t)8 * NACC * D * sizeof(float) + (dy_half ? (size_t)8 * D * 2 : 0);   // + the fp16 dy staging slabs
   auto kern = dy_half ? ln_bwd_kernel<NV, NACC, 1> : ln_bwd_kernel<NV, NACC, 0>;
   if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, 256, smem, s>>>(dy, dy_scale, x, mean, rstd, gamma, dres, dx, dx16, scale_ptr, part, M, D, round_out);

@@ -11,7 +11,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 1 -c 4 -o $O/prof_attn16 -f python tools/ncu_target.py attn16 > $O/ncu_attn16.log 2>&1
 timeout 150 ncu --set full --clock-control none -k regex:vq_fwd -c 2 -o $O/prof_vq -f python tools/ncu_target.py vq > $O/ncu_vq.log 2>&1
 timeout 150 ncu --set full --clock-control none -k regex:ln_ -c 6 -o $O/prof_ln -f python tools/ncu_target.py ln > $O/ncu_ln.log 2>&1
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 2540 -c 860 --csv --log-file $O/launches.csv \
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 2470 -c 810 --csv --log-file $O/launches.csv \
     python bench.py --steps 1 --warmup 3 --extras "" > $O/bench_under_ncu.log 2>&1
 timeout 600 python bench.py --steps 5 --warmup 3 2> $O/bench.err > $O/bench.json; cut -c1-200 $O/bench.json
 du -sh $O

@@ -465,6 +465,30 @@ def g_modes():
               f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 
 
+def g_ln16():
+    """LayerNorm forward / backward in the fp16 data path's configuration (M=131072, D=768): ms and effective HBM GB/s"""
+    import torch
+    import enhancing_transformers_b200 as etb
+    ops = etb.ops
+    M, D = 131072, 768
+    x = torch.randn(M, D, device="cuda"); g = torch.ones(D, device="cuda"); b = torch.zeros(D, device="cuda")
+    dres = torch.randn_like(x)
+    sc = ops.grad_scale(dres)
+    dy = ops.to_half(torch.randn_like(x), sc[0:1])
+    y, m, r = ops.layernorm_fwd(x, g, b, False, out_half=True)
+    ms = time_ms(lambda: ops.layernorm_fwd(x, g, b, False, out_half=True), iters=10, warm=3)
+    print(f"ln_fwd  fp16 out : {ms*1e3:7.1f} us  {M*D*6/ms/1e6:7.0f} GB/s")
+    ms = time_ms(lambda: ops.layernorm_bwd(dy, x, m, r, g, dres, want_colsum=True, half_scale=sc[0:1], dy_scale=sc[1:2]), iters=10, warm=3)
+    print(f"ln_bwd  fp16 dy, fp32+fp16 dx, colsum : {ms*1e3:7.1f} us  {M*D*16/ms/1e6:7.0f} GB/s (incl. the parameter reduce launch)")
+    dy32 = torch.randn_like(x)
+    for name, d_, kw, nbytes in (("fp32 dy, fp32 dx", dy32, {}, 16), ("fp32 dy, +colsum", dy32, dict(want_colsum=True), 16),
+                                 ("fp32 dy, +fp16 dx", dy32, dict(half_scale=sc[0:1]), 18), ("fp16 dy, fp32 dx", dy, dict(dy_scale=sc[1:2]), 14),
+                                 ("fp16 dy, +fp16 dx", dy, dict(dy_scale=sc[1:2], half_scale=sc[0:1]), 16),
+                                 ("fp16 dy, +colsum", dy, dict(dy_scale=sc[1:2], want_colsum=True), 14)):
+        ms = time_ms(lambda: ops.layernorm_bwd(d_, x, m, r, g, dres, **kw), iters=10, warm=3)
+        print(f"ln_bwd  {name:20s}: {ms*1e3:7.1f} us  {M*D*nbytes/ms/1e6:7.0f} GB/s")
+
+
 def g_attn16():
     """per-kernel time of the fp16 attention core vs the tf32 one (B from argv, default 64; base heads)"""
     import sys

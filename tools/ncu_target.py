@@ -49,8 +49,10 @@ elif what == "vq":
         ops.vq_fwd(z, E, 1, 0.25)
 elif what == "ln":
     x = torch.randn(131072, 768, device="cuda"); g = torch.ones(768, device="cuda"); b = torch.zeros(768, device="cuda")
-    dy = torch.randn_like(x); dres = torch.randn_like(x)
+    dres = torch.randn_like(x)
+    sc = ops.grad_scale(dres)
+    dy = ops.to_half(torch.randn_like(x), sc[0:1])                      # what the fp16 dgrad GEMM hands over
     for _ in range(3):
-        y, m, r = ops.layernorm_fwd(x, g, b, True)
-        ops.layernorm_bwd(dy, x, m, r, g, dres)
+        y, m, r = ops.layernorm_fwd(x, g, b, False, out_half=True)       # the fp16 data path's configuration
+        ops.layernorm_bwd(dy, x, m, r, g, dres, want_colsum=True, half_scale=sc[0:1], dy_scale=sc[1:2])
 torch.cuda.synchronize()

@@ -48,11 +48,13 @@ HEADERS = {
               "# algorithmic: 463.9 GFLOP / 0.809 GB (A 201 MB + B 3.5 MB + C 604 MB) and 618.5 GFLOP / 1.213 GB (A 805 + B 4.7 + C 403 MB).\n"
               "# traffic = dram read+write below.\n",
     "attn16": "# fp16 attention core, B=32 N=1024 heads=12 dh=64 (python tools/ncu_target.py attn16)\n"
-              "# algorithmic flops: fwd 4*B*H*N*N*dh = 103 GFLOP; bwd 10*B*H*N*N*dh = 258 GFLOP (dKV 6, dQ 4 GEMM-units of 2*N*N*dh executed: 14)\n",
+              "# algorithmic flops: fwd 4*B*H*N*N*dh = 103 GFLOP; bwd 10*B*H*N*N*dh = 258 GFLOP (dKV 8, dQ 6 GEMM-units of 2*N*N*dh executed: 14;\n"
+              "# delta = rowsum(dO*O) is computed inside the dQ kernel, which therefore runs first)\n",
     "vq": "# vq_fwd_kernel 131072 tokens x 8192 codes x 32 dims (python tools/ncu_target.py vq)\n"
           "# algorithmic: 68.7 GFLOP fp32 FMA, 34.6 MB (z in, z_q out, idx out, codebook)\n",
     "ln": "# ln_fwd / ln_bwd kernels M=131072 D=768 (python tools/ncu_target.py ln)\n"
-          "# algorithmic bytes: fwd 805 MB (read x, write y), bwd 1611 MB (read dy, x, dres; write dx)\n",
+          "# fp16 data path configuration.  algorithmic bytes: fwd 604 MB (read x fp32, write y fp16), bwd 1611 MB (read dy fp16, x, dres;\n"
+          "# write dx fp32 and its scaled fp16 copy)\n",
 }
 STALE_NOTES = {}
 OUT_NAMES = {"gemm16": "ncu_gemm_f16", "attn16": "ncu_attention_f16", "vq": "ncu_vq", "ln": "ncu_layernorm"}
@@ -126,8 +128,8 @@ def summarise_launches(src: str, dst: str, rnd: str) -> None:
                           f"of the step spent in gemm_tc_kernel: {j.get('roofline', {}).get('share_of_step')}\n")
         except Exception:
             pass
-    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none -s 2540 -c 860 python bench.py --steps 1 --warmup 3 --extras ''\n",
-             "# (B=128/GPU, base config, fp16 data path).  ~860 launches = one fwd+bwd step; per-launch times are cold-cache and\n",
+    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none -s 2470 -c 810 python bench.py --steps 1 --warmup 3 --extras ''\n",
+             "# (B=128/GPU, base config, fp16 data path).  ~806 launches = one fwd+bwd step; per-launch times are cold-cache and\n",
              "# serialised: compare SHARES with bench.py's live numbers, not absolutes.\n", bench_line]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         lines.append(f"{100 * v / total:6.2f}%  launches={cnt[k]:4d}  avg={v / cnt[k] / 1e3:9.1f} us  {k}\n")
