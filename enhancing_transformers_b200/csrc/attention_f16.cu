@@ -12,6 +12,7 @@
 //   * P / dS take half the TMEM columns and half the tcgen05.st traffic.
 // Gradients: dO carries the power-of-two gradient scale S of the backward segment (functional.py), and so do delta,
 // dS and the dq / dk / dv this kernel stores (fp16): everything is linear in dO, nothing is rescaled here.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b200 {
@@ -469,6 +470,286 @@ attn_fwd_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #ifdef B200_ATTN16_TRACE_FWD
   TRACE_DUMP();
 #endif
+}
+
+
+// =============================================================================================
+// forward, second design: TWO 128-query tiles per CTA, one softmax group of eight warps per tile, O accumulated in TMEM
+//
+// In the kernel above all 16 softmax warps work on the same score tile and move in lock-step (row max -> barrier -> exp ->
+// store -> fold): the XU pipe is saturated during the exp phase and idle otherwise (attn16_trace: 1100 of a tile's 2500
+// cycles), and both MMA issuers wait ~1800 cycles per tile.  Here a CTA owns a PAIR of query tiles that share every K / V
+// tile (half the K / V traffic per query), each tile has its own softmax group (two threads per query row, 64 scores each)
+// and the groups run out of phase: one exponentiates while the other waits for its P V / next Q K^T.  What makes the
+// per-thread state fit is that O never enters registers: P V accumulates in tensor memory across key tiles
+// (accumulate = 1) and is rescaled in place only when a row's running maximum has grown by more than 2^8 since the scale in
+// use was chosen ("lazy rescaling": P is then at most 256, well inside fp16; l is kept relative to the same stale maximum,
+// so O / l is exact) -- a rare event after the first tiles of a row.
+//   TMEM columns: S_g at g*128 (P packed fp16 over its first 64 columns), O_g at 256 + g*64
+//   warps: 0 TMA, 1 MMA issuer, 2..9 group 0, 10..17 group 1 (lane quarter = warp & 3, column half = ((warp - 2) & 7) >> 2)
+// =============================================================================================
+constexpr int kThreads2 = 576;
+constexpr int kV2Stages = 3;         // K and V rings (128-row tiles)
+constexpr float kRescaleLog2 = 8.f;  // rescale O when the row maximum has grown by more than this many powers of two
+#ifndef ATTN_FWD2_POLY_PAIRS
+#define ATTN_FWD2_POLY_PAIRS 8       // of the 32 pairs a thread exponentiates per key tile
+#endif
+
+__device__ __forceinline__ void pair_bar2(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+
+struct Fwd2Params {
+  float* lse;        // [B*heads*N]
+  int N, heads, q_pairs, kv_tiles, total_items;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kThreads2, 1)
+attn_fwd2_f16_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const Fwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  constexpr int NST = kV2Stages;
+  uint8_t* Qs = smem;                                  // [2 item buffers][2 query tiles]
+  uint8_t* Ks = smem + 4 * kTile128;                   // [NST]
+  uint8_t* Vs = smem + (4 + NST) * kTile128;           // [NST]
+  uint8_t* obox = smem + (4 + 2 * NST) * kTile128;     // 16 x 2 KB store boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obox + kBoxBytes);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* s_full = bars + 4;     // [2 groups]
+  uint64_t* p_full = bars + 6;     // [2]
+  uint64_t* pv_done = bars + 8;    // [2]
+  uint64_t* o_free = bars + 10;    // [2]
+  uint64_t* k_full = bars + 12;           // [NST]
+  uint64_t* k_empty = k_full + NST;
+  uint64_t* v_full = k_full + 2 * NST;
+  uint64_t* v_empty = k_full + 3 * NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_full + 4 * NST);
+  float* xch = reinterpret_cast<float*>(bars + 64);    // [2 tile parities][2 groups][2 halves][128] row max, then [2][2][128] row sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); mbar_init(&pv_done[s], 1); mbar_init(&o_free[s], 8);
+    }
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int inner = p.heads * DH;
+  const int T = p.kv_tiles;
+
+  if (warp == 0) {
+    // ---- TMA producer
+    uint32_t kv_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qp = w % p.q_pairs;
+      const int bh = w / p.q_pairs;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int qs = item_it & 1;
+      mbar_wait(&q_empty[qs], ((item_it >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&q_full[qs], 2 * kTile128);
+        tma_load_3d(Qs + qs * 2 * kTile128, &tmQKV, &q_full[qs], h * DH, qp * 256, b);
+        tma_load_3d(Qs + qs * 2 * kTile128 + kTile128, &tmQKV, &q_full[qs], h * DH, qp * 256 + 128, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j, ++kv_it) {
+        const int s = kv_it % NST;
+        const uint32_t ph = (kv_it / NST) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[s], kTile128);
+          tma_load_3d(Ks + s * kTile128, &tmQKV, &k_full[s], inner + h * DH, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[s], kTile128);
+          tma_load_3d(Vs + s * kTile128, &tmQKV, &v_full[s], 2 * inner + h * DH, j * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer.  Order per item: S_0(0) S_1(0), then for every key tile j and group g: P_g(j) V_j, S_g(j+1) --
+    // a group's next scores are issued right behind the P V that consumed its probabilities (P lives in the S buffer), so
+    // the two groups drift half a period apart and fill each other's tensor-pipe and XU gaps.
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, DH, 0, 1);
+    const uint64_t qd0 = kmajor_desc(Qs);
+    const uint64_t kd0 = kmajor_desc(Ks);
+    const uint64_t vd0 = mnmajor_desc(Vs);
+    uint32_t kv_it = 0, item_it = 0, tile_it = 0;      // tile_it: key tiles issued so far (per group)
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qs = item_it & 1;
+      mbar_wait(&q_full[qs], (item_it >> 1) & 1);
+      tcgen05_fence_after();
+      auto issue_s = [&](int g, uint32_t kv) {          // S_g = Q_g K^T of ring stage kv % NST
+        const int r = kv % NST;
+        if (elect_one()) {
+          const uint64_t qd = desc_advance(qd0, (qs * 2 + g) * kTile128);
+          const uint64_t kd = desc_advance(kd0, r * kTile128);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16<1>(tmem_base + g * 128, desc_advance(qd, k * kKStepK), desc_advance(kd, k * kKStepK), idesc_s, k != 0);
+          umma_commit<1>(&s_full[g]);
+          if (g == 1) umma_commit<1>(&k_empty[r]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&k_full[kv_it % NST], (kv_it / NST) & 1);
+      tcgen05_fence_after();
+      issue_s(0, kv_it);
+      issue_s(1, kv_it);
+      for (int j = 0; j < T; ++j, ++kv_it, ++tile_it) {
+        const int r = kv_it % NST;
+        for (int g = 0; g < 2; ++g) {
+          if (g == 0) mbar_wait2(&v_full[r], (kv_it / NST) & 1, &p_full[0], tile_it & 1);
+          else        mbar_wait(&p_full[1], tile_it & 1);
+          if (j == 0) mbar_wait(&o_free[g], (item_it & 1) ^ 1);     // the previous item's output has left TMEM
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t vd = desc_advance(vd0, r * kTile128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // 128 keys = 8 x UMMA_K
+              umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + k * 8, desc_advance(vd, k * kKStepMN), idesc_o, (j | k) != 0);
+            umma_commit<1>(&pv_done[g]);
+            if (g == 1) umma_commit<1>(&v_empty[r]);
+          }
+          __syncwarp();
+          if (j + 1 < T) {
+            if (g == 0) { mbar_wait(&k_full[(kv_it + 1) % NST], ((kv_it + 1) / NST) & 1); tcgen05_fence_after(); }
+            issue_s(g, kv_it + 1);
+          } else if (g == 1) {
+            if (elect_one()) umma_commit<1>(&q_empty[qs]);          // every Q K^T of the item has been issued
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ---- softmax groups
+    const int g = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int hlf = ((warp - 2) & 7) >> 2;
+    const int bar_id = 1 + g * 4 + q;                       // named barrier of the two warps that share these 32 query rows
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + g * 128;
+    const uint32_t o_addr = tmem_base + lane_off + 256 + g * 64 + hlf * 32;
+    const int row_in_tile = q * 32 + lane;
+    const float c = p.scale * kLog2eF;
+    uint32_t t_it = 0, item_it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int qp = w % p.q_pairs;
+      const int bh = w / p.q_pairs;
+      const int h = bh % p.heads, b = bh / p.heads;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < T; ++j, ++t_it) {
+        uint32_t v[64];
+        mbar_wait(&s_full[g], t_it & 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32(s_addr + hlf * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(s_addr + hlf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        const int kv_left = p.N - j * 128 - hlf * 64;       // this thread's columns >= kv_left are padding
+        if (kv_left < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= kv_left) v[i] = 0xff800000u;           // -inf
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        float* xs = xch + (t_it & 1) * 512 + g * 256;
+        xs[hlf * 128 + row_in_tile] = mx;
+        pair_bar2(bar_id);      // also orders the partner's S loads before this thread's packed P stores (they overlap its columns)
+        mx = fmaxf(mx, xs[(hlf ^ 1) * 128 + row_in_tile]);
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool grow = (mx - m_used) * c > kRescaleLog2;
+          if (__any_sync(0xffffffffu, grow)) {              // rare: bring O and l to the new maximum
+            const float m_new = grow ? mx : m_used;
+            const float alpha = ex2_approx((m_used - m_new) * c);
+            mbar_wait(&pv_done[g], (t_it - 1) & 1);          // P V of the previous key tile has landed in O
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 32; cc += 8) {
+              uint32_t ov[8];
+              tmem_ld_32x8(o_addr + cc, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st_32x8(o_addr + cc, ov);
+            }
+            tmem_st_wait();
+            l *= alpha;
+            m_used = m_new;
+          }
+        }
+        const float mc = m_used * c;
+        float sum = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int e = hh * 32 + 2 * i;
+            float a0, a1;
+            ex2_pair(poly_slot<ATTN_FWD2_POLY_PAIRS, 32>(hh * 16 + i), fmaf(__uint_as_float(v[e]), c, -mc), fmaf(__uint_as_float(v[e + 1]), c, -mc), a0, a1);
+            sum += a0; sum1 += a1;
+            pk[i] = pack_half2_sat(a0, a1);                  // <= 2^8 unless a row jumps by more than the threshold inside one tile
+          }
+          tmem_st_32x16(s_addr + hlf * 32 + hh * 16, pk);    // packed P: keys hlf*64 + hh*32 .. +32 -> columns hlf*32 + hh*16 .. +16
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        l += sum + sum1;
+      }
+      // ---- item epilogue: O / l -> fp16 -> TMA store; log-sum-exp
+      float* ls = xch + 1024 + g * 256;
+      ls[hlf * 128 + row_in_tile] = l;
+      mbar_wait(&pv_done[g], (t_it - 1) & 1);
+      tcgen05_fence_after();
+      uint32_t ov[32];
+      tmem_ld_32x32(o_addr, ov);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      pair_bar2(bar_id);
+      l += ls[(hlf ^ 1) * 128 + row_in_tile];
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      float r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(ov[i]);
+      const int row0 = qp * 256 + g * 128 + q * 32;
+      store_box_h(obox + (warp - 2) * 2048, &tmO, r, 1.f / l, h * DH + hlf * 32, row0, b, lane);
+      const int row = row0 + lane;
+      if (row < p.N && hlf == 0) p.lse[((long long)b * p.heads + h) * p.N + row] = m_used * p.scale + logf(l);
+      pair_bar2(bar_id);     // ls is rewritten by the next item only after the partner has read it
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
 }
 
 // =============================================================================================
@@ -1020,6 +1301,24 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   int rc;
   if ((rc = make_tile_map(&tmQKV, qkv, 3ll * inner, N, B, 128))) return rc;
   if ((rc = make_store_map(&tmO, out, inner, N, B, 16))) return rc;
+#ifndef ATTN_FWD_V2
+#define ATTN_FWD_V2 1
+#endif
+  static const int use_v2 = [] { const char* e = getenv("B200VQ_ATTN_FWD_V2"); return e ? atoi(e) : ATTN_FWD_V2; }();
+  if (use_v2) {
+    if ((rc = make_store_map(&tmO, out, inner, N, B, 32))) return rc;
+    Fwd2Params p2;
+    p2.lse = lse; p2.N = N; p2.heads = heads;
+    p2.q_pairs = (N + 255) / 256; p2.kv_tiles = (N + 127) / 128;
+    p2.total_items = p2.q_pairs * heads * B;
+    p2.scale = scale;
+    constexpr int smem2 = (4 + 2 * kV2Stages) * kTile128 + kBoxBytes + 512 + 1536 * 4 + 1024;
+    static_assert(smem2 <= 227 * 1024, "attention forward v2: shared-memory plan exceeds 227 KB");
+    B200_CONFIGURE_SMEM_ONCE(attn_fwd2_f16_kernel, smem2);
+    attn_fwd2_f16_kernel<<<persistent_grid(p2.total_items), kThreads2, smem2, stream>>>(tmQKV, tmO, p2);
+    B200_LAUNCH_OK("attn_fwd2_f16_kernel");
+    return 0;
+  }
   FwdParams p;
   p.lse = lse; p.N = N; p.heads = heads;
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
@@ -1032,14 +1331,6 @@ int attention_f16_forward(const void* qkv, void* out, float* lse, int B, int N, 
   return 0;
 }
 
-#ifdef B200_ATTN16_TRACE
-extern "C" int b200vq_trace16_read(long long* out) {   // out[3][2 * 64]: (event, clock) pairs per role, zero padded
-  cudaMemcpyFromSymbol(out, g_trace16, sizeof(g_trace16));
-  return 0;
-}
-#endif
-
-// dout fp16 (carrying the gradient scale), out fp16; dqkv fp16 (same scale); delta scratch fp32 [B*heads*N]
 int attention_f16_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* delta, int B, int N,
                            int heads, int dh, float scale, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
