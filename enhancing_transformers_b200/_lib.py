@@ -51,6 +51,16 @@ _SIGNATURES = {
     "b200vq_grad_scale": (c_i, [c_f, c_ll, c_i, c_f, c_f, c_sz, c_f]),
     "b200vq_bias_act": (c_i, [c_f, c_f, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f]),
     "b200vq_upfirdn2d": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "b200vq_attention_causal_fwd": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_i, c_f]),
+    "b200vq_attention_causal_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_i, c_f]),
+    "b200vq_time_mix_fwd": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_i, c_f]),
+    "b200vq_time_mix_bwd_workspace_bytes": (c_sz, [c_ll, c_i]),
+    "b200vq_time_mix_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_i, c_f]),
+    "b200vq_sqrelu": (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_f]),
+    "b200vq_token_embed_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "b200vq_token_embed_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "b200vq_copy_rows": (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f]),
+    "b200vq_decode_attention": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -73,9 +73,12 @@ int attention_backward(const float*, const void*, int, const float*, const float
                        int, int, float, int, cudaStream_t);
 int attention_f16_forward(const void*, void*, float*, int, int, int, int, float, cudaStream_t);
 int attention_f16_backward(const void*, const void*, const float*, const void*, void*, float*, int, int, int, int, float, cudaStream_t);
-int attention_exact_forward(const float*, float*, float*, int, int, int, int, float, cudaStream_t);
-int attention_exact_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float,
+int attention_exact_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int attention_exact_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float, int,
                              cudaStream_t);
+int attention_causal_forward(const float*, float*, float*, int, int, int, int, float, int, int, int, cudaStream_t);
+int attention_causal_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float, int,
+                              int, int, cudaStream_t);
 size_t vq_workspace_bytes(int, int, int);
 int vq_forward(const float*, const float*, float*, long long*, float*, int, int, int, int, float, int, void*, size_t, cudaStream_t);
 int vq_backward(const float*, const float*, const long long*, const float*, const float*, float*, float*, int, int, int, int,
@@ -93,6 +96,16 @@ size_t grad_scale_workspace_bytes();
 int bias_act(const float*, const float*, const float*, float*, long long, int, int, int, int, float, float, cudaStream_t);
 int upfirdn2d(const float*, const float*, float*, long long, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int grad_scale(const float*, long long, int, float*, void*, size_t, cudaStream_t);
+int time_mix_forward(const float*, const float*, float*, long long, int, int, int, cudaStream_t);
+size_t time_mix_bwd_workspace_bytes(long long, int);
+int time_mix_backward(const float*, const float*, const float*, float*, float*, long long, int, int, cudaStream_t);
+int sqrelu(const float*, const float*, float*, long long, int, int, cudaStream_t);
+int token_embed_forward(const long long*, const long long*, const float*, const float*, const float*, const float*, float*, int, int,
+                        int, int, int, int, cudaStream_t);
+int token_embed_backward(const long long*, const long long*, const float*, float*, float*, float*, float*, int, int, int, int, int,
+                         int, cudaStream_t);
+int copy_rows(const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int decode_attention(const float*, float*, float*, float*, int, int, int, int, int, float, cudaStream_t);
 
 }  // namespace b200
 
@@ -163,11 +176,21 @@ int b200vq_attention_f16_bwd(const void* qkv16, const void* out16, const float* 
 }
 int b200vq_attention_exact_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
                                void* stream) {
-  return attention_exact_forward(qkv, out, lse, B, N, heads, dh, scale, S(stream));
+  return attention_exact_forward(qkv, out, lse, B, N, heads, dh, scale, -1, S(stream));
 }
 int b200vq_attention_exact_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
                                float* delta, int B, int N, int heads, int dh, float scale, void* stream) {
-  return attention_exact_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, S(stream));
+  return attention_exact_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, -1, S(stream));
+}
+int b200vq_attention_causal_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
+                                int cond_len, int exact, int round_out, void* stream) {
+  return attention_causal_forward(qkv, out, lse, B, N, heads, dh, scale, cond_len, exact, round_out, S(stream));
+}
+int b200vq_attention_causal_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                                float* delta, int B, int N, int heads, int dh, float scale, int cond_len, int exact,
+                                int round_out, void* stream) {
+  return attention_causal_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, cond_len, exact, round_out,
+                                   S(stream));
 }
 size_t b200vq_vq_workspace_bytes(int M, int K, int depth) { return vq_workspace_bytes(M, K, depth); }
 int b200vq_vq_fwd(const float* z, const float* E, float* out, long long* idx, float* loss, int M, int K, int D, int depth,
@@ -215,6 +238,34 @@ int b200vq_bias_act(const float* x, const float* bias, const float* ref, float* 
 int b200vq_upfirdn2d(const float* in, const float* kernel, float* out, long long planes, int in_h, int in_w, int kh, int kw, int up_x,
                      int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream) {
   return upfirdn2d(in, kernel, out, planes, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, S(stream));
+}
+
+int b200vq_time_mix_fwd(const float* x, const float* w, float* y, long long M, int T, int C, int round_out, void* stream) {
+  return time_mix_forward(x, w, y, M, T, C, round_out, S(stream));
+}
+size_t b200vq_time_mix_bwd_workspace_bytes(long long M, int C) { return time_mix_bwd_workspace_bytes(M, C); }
+int b200vq_time_mix_bwd(const float* g, const float* x, const float* w, float* gx, float* gw_part, long long M, int T, int C,
+                        void* stream) {
+  return time_mix_backward(g, x, w, gx, gw_part, M, T, C, S(stream));
+}
+int b200vq_sqrelu(const float* x, const float* g, float* y, long long n, int grad, int round_out, void* stream) {
+  return sqrelu(x, g, y, n, grad, round_out, S(stream));
+}
+int b200vq_token_embed_fwd(const long long* conds, const long long* codes, const float* Wc, const float* pos_c, const float* Wi,
+                           const float* pos_i, float* x, int B, int Tc, int Ti, int C, int Vc, int Vi, void* stream) {
+  return token_embed_forward(conds, codes, Wc, pos_c, Wi, pos_i, x, B, Tc, Ti, C, Vc, Vi, S(stream));
+}
+int b200vq_token_embed_bwd(const long long* conds, const long long* codes, const float* g, float* gWc, float* gpos_c, float* gWi,
+                           float* gpos_i, int B, int Tc, int Ti, int C, int Vc, int Vi, void* stream) {
+  return token_embed_backward(conds, codes, g, gWc, gpos_c, gWi, gpos_i, B, Tc, Ti, C, Vc, Vi, S(stream));
+}
+int b200vq_copy_rows(const float* src, float* dst, int B, int T_src, int T_dst, int off_src, int off_dst, int n, int C,
+                     void* stream) {
+  return copy_rows(src, dst, B, T_src, T_dst, off_src, off_dst, n, C, S(stream));
+}
+int b200vq_decode_attention(const float* qkv, float* cache_k, float* cache_v, float* out, int B, int heads, int hs, int Tmax,
+                            int pos, float scale, void* stream) {
+  return decode_attention(qkv, cache_k, cache_v, out, B, heads, hs, Tmax, pos, scale, S(stream));
 }
 
 }  // extern "C"

@@ -9,9 +9,12 @@
 
 namespace b200 {
 
-int attention_forward_tc(const float*, void*, int, float*, int, int, int, int, float, int, cudaStream_t);
+int attention_forward_tc(const float*, void*, int, float*, int, int, int, int, float, int, int, cudaStream_t);
 int attention_backward_tc(const float*, const float*, const float*, const float*, void*, int, const float*, int, int, int, int,
-                          float, int, cudaStream_t);
+                          float, int, int, cudaStream_t);
+int attention_exact_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int attention_exact_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, float, int,
+                             cudaStream_t);
 
 // delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d].  HBM-bound: one float4 of O and dO per thread, dh/4 adjacent
 // lanes per (row, head) reduced with shuffles, so a warp streams 512 contiguous bytes of each tensor.
@@ -53,7 +56,7 @@ int attention_forward(const float* qkv, void* out, int out_half, float* lse, int
                       int round_out, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
-  return attention_forward_tc(qkv, out, out_half, lse, B, N, heads, dh, scale, round_out, stream);
+  return attention_forward_tc(qkv, out, out_half, lse, B, N, heads, dh, scale, round_out, -1, stream);
 }
 
 int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
@@ -88,7 +91,32 @@ int attention_backward(const float* qkv, const void* out, int out_half, const fl
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   int rc = attention_delta(out, out_half, dout, 0, delta, B, N, heads, dh, stream);
   if (rc) return rc;
-  return attention_backward_tc(qkv, dout, lse, delta, dqkv, dqkv_half, dqkv_scale, B, N, heads, dh, scale, round_out, stream);
+  return attention_backward_tc(qkv, dout, lse, delta, dqkv, dqkv_half, dqkv_scale, B, N, heads, dh, scale, round_out, -1, stream);
+}
+
+// Stage-2 attention (reference enhancing/modules/stage2/layers.py:76-89): causal mask whose first cond_len tokens (the
+// condition prefix) see each other fully -- query q attends to key k iff k <= max(q, cond_len - 1).  Same packed qkv layout
+// as the stage-1 core (the reference's (T, B*nh, hs) views are that layout transposed).  exact != 0: 3xTF32 mma.sync kernels
+// (precision="parity"); otherwise the tcgen05 kind::tf32 kernels with the mask folded into their padding logic.
+int attention_causal_forward(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale, int cond_len,
+                             int exact, int round_out, cudaStream_t stream) {
+  B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  B200_CHECK_ARG(dh == 64 || dh == 32, "attention: head size must be 32 or 64 (got %d)", dh);
+  B200_CHECK_ARG(cond_len >= 0 && cond_len <= N, "attention: cond_len %d outside [0, %d]", cond_len, N);
+  if (exact) return attention_exact_forward(qkv, out, lse, B, N, heads, dh, scale, cond_len, stream);
+  return attention_forward_tc(qkv, out, 0, lse, B, N, heads, dh, scale, round_out, cond_len, stream);
+}
+
+int attention_causal_backward(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv, float* delta,
+                              int B, int N, int heads, int dh, float scale, int cond_len, int exact, int round_out,
+                              cudaStream_t stream) {
+  B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  B200_CHECK_ARG(dh == 64 || dh == 32, "attention: head size must be 32 or 64 (got %d)", dh);
+  B200_CHECK_ARG(cond_len >= 0 && cond_len <= N, "attention: cond_len %d outside [0, %d]", cond_len, N);
+  if (exact) return attention_exact_backward(qkv, out, lse, dout, dqkv, delta, B, N, heads, dh, scale, cond_len, stream);
+  int rc = attention_delta(out, 0, dout, 0, delta, B, N, heads, dh, stream);
+  if (rc) return rc;
+  return attention_backward_tc(qkv, dout, lse, delta, dqkv, 0, nullptr, B, N, heads, dh, scale, round_out, cond_len, stream);
 }
 
 }  // namespace b200

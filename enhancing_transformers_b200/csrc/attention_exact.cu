@@ -110,7 +110,7 @@ __device__ __forceinline__ void acc_to_a(uint32_t (&a)[4], float c0, float c1, f
 template <int DH>
 __global__ void __launch_bounds__(256)
 attn_exact_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int N, int heads,
-                float scale) {
+                float scale, int cond) {
   constexpr int LDS = DH + 4;
   constexpr int TILE = 64 * LDS;
   extern __shared__ __align__(16) float sm[];   // K[2][TILE], V[2][TILE]
@@ -135,7 +135,13 @@ attn_exact_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
   for (int i = 0; i < DH / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  const int ntiles = (N + 63) / 64;
+  // cond >= 0: stage-2 mask (reference stage2/layers.py:43-48,83-85): query q sees key k iff k <= max(q, cond - 1)
+  // (causal, with the first `cond` condition tokens fully visible to each other).  Key 0 is visible to every row, so the
+  // running maximum is finite after the first tile and fully masked tiles contribute exp2(-inf) = 0.
+  const bool masked = cond >= 0;
+  const int lim0 = masked ? max(q0 + g, cond - 1) : N, lim1 = masked ? max(q0 + g + 8, cond - 1) : N;
+  int ntiles = (N + 63) / 64;
+  if (masked) ntiles = min(ntiles, max(min(N - 1, (int)blockIdx.x * 128 + 127), cond - 1) / 64 + 1);   // tiles past the CTA's last visible key
   load_tile<DH, 64, 256>(Ks, kbase, ld, 0, N, tid);
   load_tile<DH, 64, 256>(Vs, vbase, ld, 0, N, tid);
   cpa_commit();
@@ -158,6 +164,16 @@ attn_exact_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
         const int key = j * 64 + nt * 8 + 2 * t;
         if (key >= N) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
         if (key + 1 >= N) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
+    }
+    if (masked && j * 64 + 63 > min(lim0, lim1)) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = j * 64 + nt * 8 + 2 * t;
+        if (key > lim0) s[nt][0] = -INFINITY;
+        if (key + 1 > lim0) s[nt][1] = -INFINITY;
+        if (key > lim1) s[nt][2] = -INFINITY;
+        if (key + 1 > lim1) s[nt][3] = -INFINITY;
       }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -212,7 +228,7 @@ attn_exact_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
 template <int DH>
 __global__ void __launch_bounds__(128)
 attn_exact_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                    const float* __restrict__ delta, float* __restrict__ dqkv, int N, int heads, float scale) {
+                    const float* __restrict__ delta, float* __restrict__ dqkv, int N, int heads, float scale, int cond) {
   constexpr int LDS = DH + 4;
   constexpr int TILE = 64 * LDS;
   extern __shared__ __align__(16) float sm[];   // Q[2][TILE], dO[2][TILE], lse[2][64], delta[2][64]
@@ -250,9 +266,14 @@ attn_exact_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
     cpa_commit();
   };
   const int ntiles = (N + 63) / 64;
-  stage(0, 0);
-  for (int j = 0; j < ntiles; ++j) {
-    const int buf = j & 1;
+  // stage-2 mask: key k receives from query q iff k <= max(q, cond - 1).  A key tile that starts at or past `cond` is
+  // invisible to every query tile before its own.
+  const bool masked = cond >= 0;
+  const int jbeg = (masked && (int)blockIdx.x * 64 >= cond) ? (int)blockIdx.x : 0;
+  const int kr0 = k0 + g, kr1 = k0 + g + 8;
+  stage(jbeg, 0);
+  for (int j = jbeg; j < ntiles; ++j) {
+    const int buf = (j - jbeg) & 1;
     cpa_wait<0>();
     __syncthreads();
     if (j + 1 < ntiles) stage(j + 1, buf ^ 1);
@@ -268,6 +289,13 @@ attn_exact_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
       const float la = Ls[buf * 64 + nt * 8 + 2 * t], lbb = Ls[buf * 64 + nt * 8 + 2 * t + 1];
       s[nt][0] = exp2f(s[nt][0] * c - la);  s[nt][1] = exp2f(s[nt][1] * c - lbb);
       s[nt][2] = exp2f(s[nt][2] * c - la);  s[nt][3] = exp2f(s[nt][3] * c - lbb);
+      if (masked) {
+        const int va = max(j * 64 + nt * 8 + 2 * t, cond - 1), vb = max(j * 64 + nt * 8 + 2 * t + 1, cond - 1);   // last key each query sees
+        if (kr0 > va) s[nt][0] = 0.f;
+        if (kr0 > vb) s[nt][1] = 0.f;
+        if (kr1 > va) s[nt][2] = 0.f;
+        if (kr1 > vb) s[nt][3] = 0.f;
+      }
       acc_to_a(pf[nt], s[nt][0], s[nt][1], s[nt][2], s[nt][3]);
     }
     mma_p_x_tile<DH>(dv, pf, dO, lane);              // dV += P^T dO
@@ -307,7 +335,7 @@ attn_exact_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
 template <int DH>
 __global__ void __launch_bounds__(128)
 attn_exact_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                   const float* __restrict__ delta, float* __restrict__ dqkv, int N, int heads, float scale) {
+                   const float* __restrict__ delta, float* __restrict__ dqkv, int N, int heads, float scale, int cond) {
   constexpr int LDS = DH + 4;
   constexpr int TILE = 64 * LDS;
   extern __shared__ __align__(16) float sm[];   // K[2][TILE], V[2][TILE]
@@ -337,7 +365,10 @@ attn_exact_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
 
-  const int ntiles = (N + 63) / 64;
+  const bool masked = cond >= 0;
+  const int lim0 = masked ? max(r0, cond - 1) : N, lim1 = masked ? max(r1, cond - 1) : N;
+  int ntiles = (N + 63) / 64;
+  if (masked) ntiles = min(ntiles, max(min(N - 1, (int)blockIdx.x * 64 + 63), cond - 1) / 64 + 1);
   load_tile<DH, 64, 128>(Ks, kbase, ld, 0, N, tid);
   load_tile<DH, 64, 128>(Vs, vbase, ld, 0, N, tid);
   cpa_commit();
@@ -360,8 +391,8 @@ attn_exact_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
     for (int nt = 0; nt < 8; ++nt) {
       const int key = j * 64 + nt * 8 + 2 * t;
       const bool ka = key < N, kb = key + 1 < N;
-      const float p0 = ka ? exp2f(s[nt][0] * c - lse0) : 0.f, p1 = kb ? exp2f(s[nt][1] * c - lse0) : 0.f;
-      const float p2 = ka ? exp2f(s[nt][2] * c - lse1) : 0.f, p3 = kb ? exp2f(s[nt][3] * c - lse1) : 0.f;
+      const float p0 = (ka && key <= lim0) ? exp2f(s[nt][0] * c - lse0) : 0.f, p1 = (kb && key + 1 <= lim0) ? exp2f(s[nt][1] * c - lse0) : 0.f;
+      const float p2 = (ka && key <= lim1) ? exp2f(s[nt][2] * c - lse1) : 0.f, p3 = (kb && key + 1 <= lim1) ? exp2f(s[nt][3] * c - lse1) : 0.f;
       acc_to_a(pf[nt], p0 * (dp[nt][0] - e0), p1 * (dp[nt][1] - e0), p2 * (dp[nt][2] - e1), p3 * (dp[nt][3] - e1));
     }
     mma_p_x_tile<DH>(dq, pf, Ks + buf * TILE, lane);        // dQ += dS K
@@ -378,18 +409,18 @@ attn_exact_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-static int exact_fwd_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, cudaStream_t s) {
+static int exact_fwd_launch(const float* qkv, float* out, float* lse, int B, int N, int heads, float scale, int cond, cudaStream_t s) {
   constexpr size_t smem = 4 * 64 * (DH + 4) * sizeof(float);
   auto kern = attn_exact_fwd_kernel<DH>;
   B200_CONFIGURE_SMEM_ONCE(kern, smem);
-  kern<<<dim3((N + 127) / 128, heads, B), 256, smem, s>>>(qkv, out, lse, N, heads, scale);
+  kern<<<dim3((N + 127) / 128, heads, B), 256, smem, s>>>(qkv, out, lse, N, heads, scale, cond);
   B200_LAUNCH_OK("attn_exact_fwd_kernel");
   return 0;
 }
 
 template <int DH>
 static int exact_bwd_launch(const float* qkv, const float* dout, const float* lse, const float* delta, float* dqkv, int B,
-                            int N, int heads, float scale, cudaStream_t s) {
+                            int N, int heads, float scale, int cond, cudaStream_t s) {
   constexpr size_t smem_kv = (4 * 64 * (DH + 4) + 256) * sizeof(float);
   constexpr size_t smem_q = 4 * 64 * (DH + 4) * sizeof(float);
   auto k1 = attn_exact_bwd_dkv_kernel<DH>;
@@ -397,9 +428,9 @@ static int exact_bwd_launch(const float* qkv, const float* dout, const float* ls
   B200_CONFIGURE_SMEM_ONCE(k1, smem_kv);
   B200_CONFIGURE_SMEM_ONCE(k2, smem_q);
   const dim3 grid((N + 63) / 64, heads, B);
-  k1<<<grid, 128, smem_kv, s>>>(qkv, dout, lse, delta, dqkv, N, heads, scale);
+  k1<<<grid, 128, smem_kv, s>>>(qkv, dout, lse, delta, dqkv, N, heads, scale, cond);
   B200_LAUNCH_OK("attn_exact_bwd_dkv_kernel");
-  k2<<<grid, 128, smem_q, s>>>(qkv, dout, lse, delta, dqkv, N, heads, scale);
+  k2<<<grid, 128, smem_q, s>>>(qkv, dout, lse, delta, dqkv, N, heads, scale, cond);
   B200_LAUNCH_OK("attn_exact_bwd_dq_kernel");
   return 0;
 }
@@ -408,24 +439,27 @@ static int exact_bwd_launch(const float* qkv, const float* dout, const float* ls
 int attention_delta(const void* out, int out_half, const void* dout, int dout_half, float* delta, int B, int N, int heads, int dh,
                     cudaStream_t stream);
 
+// cond_len < 0: no mask (stage 1).  cond_len >= 0: the stage-2 mask, causal with a fully visible prefix of cond_len tokens.
 int attention_exact_forward(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
-                            cudaStream_t stream) {
+                            int cond_len, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
-  if (dh == 64) return exact_fwd_launch<64>(qkv, out, lse, B, N, heads, scale, stream);
-  return exact_fwd_launch<32>(qkv, out, lse, B, N, heads, scale, stream);
+  B200_CHECK_ARG(cond_len <= N, "attention: cond_len %d exceeds the sequence length %d", cond_len, N);
+  if (dh == 64) return exact_fwd_launch<64>(qkv, out, lse, B, N, heads, scale, cond_len, stream);
+  return exact_fwd_launch<32>(qkv, out, lse, B, N, heads, scale, cond_len, stream);
 }
 
 int attention_exact_backward(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv, float* delta,
-                             int B, int N, int heads, int dh, float scale, cudaStream_t stream) {
+                             int B, int N, int heads, int dh, float scale, int cond_len, cudaStream_t stream) {
   B200_CHECK_ARG(B > 0 && N > 0 && heads > 0, "attention: empty problem");
+  B200_CHECK_ARG(cond_len <= N, "attention: cond_len %d exceeds the sequence length %d", cond_len, N);
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
   int rc = attention_delta(out, 0, dout, 0, delta, B, N, heads, dh, stream);
   if (rc) return rc;
-  if (dh == 64) return exact_bwd_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, stream);
-  return exact_bwd_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, stream);
+  if (dh == 64) return exact_bwd_launch<64>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, cond_len, stream);
+  return exact_bwd_launch<32>(qkv, dout, lse, delta, dqkv, B, N, heads, scale, cond_len, stream);
 }
 
 }  // namespace b200

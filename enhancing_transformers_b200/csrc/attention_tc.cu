@@ -119,6 +119,7 @@ struct AttnTcParams {
   int q_tiles, kv_tiles, total_items;
   float scale;
   int round_out;
+  int cond;          // < 0: no mask; >= 0: stage-2 mask, query q sees key k iff k <= max(q, cond - 1) (stage2/layers.py:43-48)
 };
 
 template <int DH>
@@ -310,7 +311,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
       for (int j = 0; j < T; ++j, ++t_it) {
         const int s = t_it & 1;
         const uint32_t sa = tmem_base + lane_off + s * 128 + half * 64;
-        const int kv_left = p.N - j * 128 - half * 64;   // this thread's columns >= kv_left are padding
+        int kv_left = p.N - j * 128 - half * 64;         // this thread's columns >= kv_left are padding
+        // stage-2 mask: the row's last visible key is max(row, cond - 1).  Key 0 is visible to every row, so the running
+        // maximum is finite after the first tile and a fully masked tile contributes exp2(-inf) = 0 with alpha = 1.
+        if (p.cond >= 0) kv_left = min(kv_left, max(qt * 128 + row_in_tile, p.cond - 1) + 1 - j * 128 - half * 64);
         if (warp == 2) TRACE(0, 230); else if (warp == 6) TRACE(1, 230);
         if (kv_left < 64) {                                 // only the last tile of a ragged sequence has padded keys
 #pragma unroll
@@ -420,7 +424,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 
 template <int DH>
 static int attn_fwd_tc_launch(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, float scale,
-                              int round_out, cudaStream_t stream) {
+                              int round_out, int cond, cudaStream_t stream) {
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
   CUtensorMap tmQK, tmV;
@@ -442,7 +446,7 @@ static int attn_fwd_tc_launch(const float* qkv, void* out, int out_half, float* 
   p.out = static_cast<float*>(out); p.out_half = out_half; p.lse = lse; p.B = B; p.N = N; p.heads = heads;
   p.q_tiles = (N + 127) / 128; p.kv_tiles = (N + 127) / 128;
   p.total_items = p.q_tiles * heads * B;
-  p.scale = scale; p.round_out = round_out;
+  p.scale = scale; p.round_out = round_out; p.cond = cond;
   CUtensorMap tmO;
   {
     const unsigned long long dims[3] = {(unsigned long long)inner, (unsigned long long)N, (unsigned long long)B};
@@ -487,6 +491,7 @@ struct AttnBwdParams {
   int tiles128, sub64, total_items;
   float scale;
   int round_out;
+  int cond;             // stage-2 mask, as in AttnTcParams
 };
 
 template <int DH>
@@ -697,14 +702,28 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
         tmem_ld_wait();
         if (warp == 2) TRACE(2, 240);
+        if (p.cond < 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float Lj = __shfl_sync(0xffffffffu, myL, j);
-          const float Ej = __shfl_sync(0xffffffffu, myE, j);
-          const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Lj));
-          const float ds = pr * (__uint_as_float(g[j]) - Ej);
-          v[j] = tf32_bits_for_mma(pr);
-          g[j] = tf32_bits_for_mma(ds);
+          for (int j = 0; j < 32; ++j) {
+            const float Lj = __shfl_sync(0xffffffffu, myL, j);
+            const float Ej = __shfl_sync(0xffffffffu, myE, j);
+            const float pr = ex2_approx(fmaf(__uint_as_float(v[j]), c, -Lj));
+            const float ds = pr * (__uint_as_float(g[j]) - Ej);
+            v[j] = tf32_bits_for_mma(pr);
+            g[j] = tf32_bits_for_mma(ds);
+          }
+        } else {      // stage-2 mask: this thread's key row receives from query column qj iff key <= max(qj, cond - 1)
+          const int key = kt * 128 + q * 32 + lane;
+          const int q0c = i * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float Lj = __shfl_sync(0xffffffffu, myL, j);
+            const float Ej = __shfl_sync(0xffffffffu, myE, j);
+            const float pr = key <= max(q0c + j, p.cond - 1) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -Lj)) : 0.f;
+            const float ds = pr * (__uint_as_float(g[j]) - Ej);
+            v[j] = tf32_bits_for_mma(pr);
+            g[j] = tf32_bits_for_mma(ds);
+          }
         }
         if (warp == 2) TRACE(2, 260);
         tmem_st_32x32(tmem_base + lane_off + col, v);
@@ -920,7 +939,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
         mbar_wait(&s_full[s], (t_it >> 1) & 1);
         tcgen05_fence_after();
         const int col = s * 64 + half * 32;
-        const int kv_left = p.N - i * 64 - half * 32;
+        int kv_left = p.N - i * 64 - half * 32;
+        if (p.cond >= 0) kv_left = min(kv_left, max(row, p.cond - 1) + 1 - i * 64 - half * 32);   // stage-2 mask
         uint32_t v[32], g[32];
         tmem_ld_32x32(tmem_base + lane_off + col, v);
         tmem_ld_32x32(tmem_base + lane_off + 128 + col, g);
@@ -1014,7 +1034,8 @@ static int make_mnmajor_map(CUtensorMap* out, const float* ptr, long long ld, in
 
 template <int DH>
 static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* lse, const float* delta, void* dqkv, int out_half,
-                              const float* out_scale, int B, int N, int heads, float scale, int round_out, cudaStream_t stream) {
+                              const float* out_scale, int B, int N, int heads, float scale, int round_out, int cond,
+                              cudaStream_t stream) {
   const int inner = heads * DH;
   const long long ld = 3ll * inner;
   CUtensorMap tmKV128, tmQ64, tmDO64, tmQM, tmDOM, tmDO128, tmOut;
@@ -1036,7 +1057,7 @@ static int attn_bwd_tc_launch(const float* qkv, const float* dout, const float* 
   p.B = B; p.N = N; p.heads = heads;
   p.tiles128 = (N + 127) / 128; p.sub64 = (N + 63) / 64;
   p.total_items = p.tiles128 * heads * B;
-  p.scale = scale; p.round_out = round_out;
+  p.scale = scale; p.round_out = round_out; p.cond = cond;
   constexpr int smem_kv = 2 * 128 * DH * 4 + 8 * 64 * DH * 4 + kOutBoxBytes + 256 + 1024;
   constexpr int smem_q = 2 * 128 * DH * 4 + 6 * 64 * DH * 4 + kOutBoxBytes + 256 + 1024;
   auto k1 = attn_bwd_dkv_tc_kernel<DH>;
@@ -1061,19 +1082,22 @@ extern "C" int b200vq_trace_read(long long* out) {   // out[3][2 * 36]: (event, 
 #endif
 
 int attention_backward_tc(const float* qkv, const float* dout, const float* lse, const float* delta, void* dqkv, int out_half,
-                          const float* out_scale, int B, int N, int heads, int dh, float scale, int round_out, cudaStream_t stream) {
+                          const float* out_scale, int B, int N, int heads, int dh, float scale, int round_out, int cond_len,
+                          cudaStream_t stream) {
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
                  "attention: qkv/dout must be 16-byte aligned");
-  if (dh == 64) return attn_bwd_tc_launch<64>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, stream);
-  return attn_bwd_tc_launch<32>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, stream);
+  B200_CHECK_ARG(cond_len <= N, "attention: cond_len %d exceeds the sequence length %d", cond_len, N);
+  if (dh == 64) return attn_bwd_tc_launch<64>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, cond_len, stream);
+  return attn_bwd_tc_launch<32>(qkv, dout, lse, delta, dqkv, out_half, out_scale, B, N, heads, scale, round_out, cond_len, stream);
 }
 
 int attention_forward_tc(const float* qkv, void* out, int out_half, float* lse, int B, int N, int heads, int dh, float scale,
-                         int round_out, cudaStream_t stream) {
+                         int round_out, int cond_len, cudaStream_t stream) {
+  B200_CHECK_ARG(cond_len <= N, "attention: cond_len %d exceeds the sequence length %d", cond_len, N);
   B200_CHECK_ARG(dh == 64 || dh == 32, "attention: dim_head must be 32 or 64 (got %d)", dh);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "attention: qkv must be 16-byte aligned");
-  if (dh == 64) return attn_fwd_tc_launch<64>(qkv, out, out_half, lse, B, N, heads, scale, round_out, stream);
-  return attn_fwd_tc_launch<32>(qkv, out, out_half, lse, B, N, heads, scale, round_out, stream);
+  if (dh == 64) return attn_fwd_tc_launch<64>(qkv, out, out_half, lse, B, N, heads, scale, round_out, cond_len, stream);
+  return attn_fwd_tc_launch<32>(qkv, out, out_half, lse, B, N, heads, scale, round_out, cond_len, stream);
 }
 
 }  // namespace b200

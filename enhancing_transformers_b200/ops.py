@@ -363,3 +363,101 @@ def add_rows_mod(x: Tensor, table: Tensor) -> Tensor:
     out = torch.empty_like(x)
     _lib.check(_lib.lib().b200vq_add_rows_mod(_p(x), _p(table), _p(out), M, D, R, _stream()), "add_rows_mod")
     return out
+
+
+# ------------------------------------------------------------------- stage-2 transformer
+def attention_causal_fwd(qkv: Tensor, B: int, N: int, heads: int, dh: int, scale: float, cond_len: int, exact: bool,
+                         round_out: bool = False) -> Tuple[Tensor, Tensor]:
+    """masked attention core of the stage-2 blocks: query q sees key k iff k <= max(q, cond_len - 1)"""
+    _req(qkv, "qkv")
+    out = torch.empty(B * N, heads * dh, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_attention_causal_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, dh, scale, int(cond_len), int(exact),
+                                                      int(round_out), _stream()), "attention_causal_fwd")
+    return out, lse
+
+
+def attention_causal_bwd(qkv: Tensor, out: Tensor, lse: Tensor, dout: Tensor, B: int, N: int, heads: int, dh: int, scale: float,
+                         cond_len: int, exact: bool, round_out: bool = False) -> Tensor:
+    _req(qkv, "qkv"); _req(out, "out"); _req(lse, "lse"); _req(dout, "dout")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _lib.check(_lib.lib().b200vq_attention_causal_bwd(_p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(delta), B, N, heads, dh, scale,
+                                                      int(cond_len), int(exact), int(round_out), _stream()), "attention_causal_bwd")
+    return dqkv
+
+
+def time_mix_fwd(x: Tensor, w: Tensor, T: int, round_out: bool = False) -> Tensor:
+    """x [M = B*T, C], w [C] -> x * w + shift(x) * (1 - w)"""
+    _req(x, "x"); _req(w, "time_mix")
+    M, C = x.shape
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().b200vq_time_mix_fwd(_p(x), _p(w), _p(y), M, T, C, int(round_out), _stream()), "time_mix_fwd")
+    return y
+
+
+def time_mix_bwd(g: Tensor, x: Tensor, w: Tensor, T: int) -> Tuple[Tensor, Tensor]:
+    """-> (gx, gw)"""
+    _req(g, "g"); _req(x, "x"); _req(w, "time_mix")
+    M, C = x.shape
+    L = _lib.lib()
+    part = torch.empty(L.b200vq_time_mix_bwd_workspace_bytes(M, C) // (4 * C), C, device=x.device, dtype=torch.float32)
+    gx = torch.empty_like(x)
+    _lib.check(L.b200vq_time_mix_bwd(_p(g), _p(x), _p(w), _p(gx), _p(part), M, T, C, _stream()), "time_mix_bwd")
+    return gx, colsum(part)
+
+
+def sqrelu(x: Tensor, g: Optional[Tensor] = None, round_out: bool = False) -> Tensor:
+    """g is None: relu(x)^2; otherwise g * 2 relu(x) (x the pre-activation)"""
+    _req(x, "x"); _req(g, "g")
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().b200vq_sqrelu(_p(x), _p(g), _p(y), x.numel(), int(g is not None), int(round_out), _stream()), "sqrelu")
+    return y
+
+
+def token_embed_fwd(conds: Tensor, codes: Tensor, Wc: Tensor, pos_c: Tensor, Wi: Tensor, pos_i: Tensor) -> Tensor:
+    """conds int64 [B, Tc], codes int64 [B, Ti] -> x [B * (Tc + Ti), C]"""
+    _req(conds, "conds", torch.int64); _req(codes, "codes", torch.int64)
+    _req(Wc, "tok_emb_cond.weight"); _req(pos_c, "pos_emb_cond"); _req(Wi, "tok_emb_code.weight"); _req(pos_i, "pos_emb_code")
+    B, Tc = conds.shape
+    Ti = codes.shape[1]
+    C = Wi.shape[1]
+    x = torch.empty(B * (Tc + Ti), C, device=Wi.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_token_embed_fwd(_p(conds), _p(codes), _p(Wc), _p(pos_c), _p(Wi), _p(pos_i), _p(x), B, Tc, Ti, C,
+                                                 Wc.shape[0], Wi.shape[0], _stream()), "token_embed_fwd")
+    return x
+
+
+def token_embed_bwd(conds: Tensor, codes: Tensor, g: Tensor, Vc: int, Vi: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (gWc [Vc, C], gpos_c [Tc, C], gWi [Vi, C], gpos_i [Ti, C])"""
+    _req(conds, "conds", torch.int64); _req(codes, "codes", torch.int64); _req(g, "g")
+    B, Tc = conds.shape
+    Ti = codes.shape[1]
+    C = g.shape[-1]
+    gWc = torch.empty(Vc, C, device=g.device, dtype=torch.float32)
+    gWi = torch.empty(Vi, C, device=g.device, dtype=torch.float32)
+    gpc = torch.empty(Tc, C, device=g.device, dtype=torch.float32)
+    gpi = torch.empty(Ti, C, device=g.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_token_embed_bwd(_p(conds), _p(codes), _p(g), _p(gWc), _p(gpc), _p(gWi), _p(gpi), B, Tc, Ti, C, Vc, Vi,
+                                                 _stream()), "token_embed_bwd")
+    return gWc, gpc, gWi, gpi
+
+
+def copy_rows(src: Tensor, B: int, T_src: int, T_dst: int, off_src: int, off_dst: int, n: int) -> Tensor:
+    """src [B*T_src, C] -> dst [B*T_dst, C]: rows [off_dst, off_dst + n) of every batch entry copied from
+    [off_src, off_src + n), the rest zero"""
+    _req(src, "src")
+    C = src.shape[-1]
+    dst = torch.empty(B * T_dst, C, device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_copy_rows(_p(src), _p(dst), B, T_src, T_dst, off_src, off_dst, n, C, _stream()), "copy_rows")
+    return dst
+
+
+def decode_attention(qkv: Tensor, cache_k: Tensor, cache_v: Tensor, heads: int, hs: int, pos: int, scale: float) -> Tensor:
+    """one sampling step: qkv [B, 3*C]; caches [B, Tmax, C] (row `pos` is written); -> out [B, C]"""
+    _req(qkv, "qkv"); _req(cache_k, "cache_k"); _req(cache_v, "cache_v")
+    B = qkv.shape[0]
+    out = torch.empty(B, heads * hs, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200vq_decode_attention(_p(qkv), _p(cache_k), _p(cache_v), _p(out), B, heads, hs, cache_k.shape[1], int(pos),
+                                                  scale, _stream()), "decode_attention")
+    return out

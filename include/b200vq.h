@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200VQ_VERSION 201 /* 0.2.1 */
+#define B200VQ_VERSION 202 /* 0.2.2 */
 
 int b200vq_version(void);
 const char* b200vq_last_error(void);
@@ -179,6 +179,43 @@ int b200vq_bias_act(const float* x, const float* bias, const float* ref, float* 
 int b200vq_upfirdn2d(const float* in, const float* kernel, float* out, long long planes, int in_h, int in_w, int kh, int kw,
                      int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                      void* stream);
+
+/* ---- stage-2 transformer (reference enhancing/modules/stage2/layers.py) --------------------
+ * attention_causal: the stage-1 attention contract (same packed qkv / out / lse / delta layouts, fp32) with the stage-2
+ *   mask of layers.py:43-48,83-85: query q attends to key k iff k <= max(q, cond_len - 1) -- causal, the cond_len
+ *   condition tokens fully visible to each other.  exact != 0: error-compensated 3xTF32 (precision="parity");
+ *   otherwise the tcgen05 kind::tf32 kernels (round_out as in b200vq_attention_fwd).  dh (the head size
+ *   embed_dim / n_heads) must be 32 or 64.
+ * time_mix: y = x * w + shift(x) * (1 - w), shift = one step along T with a zero first row (layers.py:50-58), bit-identical
+ *   to the reference's four fp32 tensor ops.  x, y [M = B*T, C]; w [C].
+ *   bwd: gx likewise; gw_part [ceil(M / 64), C] holds per-64-row partial sums of g * (x - shift(x)) -- b200vq_colsum over
+ *   it is the gradient of w.
+ * sqrelu: grad 0: y = relu(x)^2 (layers.py:108); grad 1: y = g * 2 relu(x), x the pre-activation.
+ * token_embed: x[b] = cat(Wc[conds[b]] + pos_c, Wi[codes[b]] + pos_i) (layers.py:199-206); conds int64 [B, Tc], codes
+ *   int64 [B, Ti], x [B, Tc + Ti, C].  bwd: gWc / gWi are zero-filled then accumulated, gpos_* = sum over the batch.
+ * copy_rows: dst[b, t] = src[b, t - off_dst + off_src] for off_dst <= t < off_dst + n, else 0 (the window
+ *   x[:, cond-1:-1] of layers.py:210 and its zero-padded gradient).
+ * decode_attention: one sampling step of layers.py:66-81 (use_cache with layer_past): appends the k / v thirds of
+ *   qkv [B, 3*C] to cache_k / cache_v [B, Tmax, C] at row `pos` and writes softmax(q K^T * scale) V over rows 0..pos
+ *   to out [B, C]. */
+int b200vq_attention_causal_fwd(const float* qkv, float* out, float* lse, int B, int N, int heads, int dh, float scale,
+                                int cond_len, int exact, int round_out, void* stream);
+int b200vq_attention_causal_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                                float* delta, int B, int N, int heads, int dh, float scale, int cond_len, int exact,
+                                int round_out, void* stream);
+int b200vq_time_mix_fwd(const float* x, const float* w, float* y, long long M, int T, int C, int round_out, void* stream);
+size_t b200vq_time_mix_bwd_workspace_bytes(long long M, int C);
+int b200vq_time_mix_bwd(const float* g, const float* x, const float* w, float* gx, float* gw_part, long long M, int T, int C,
+                        void* stream);
+int b200vq_sqrelu(const float* x, const float* g, float* y, long long n, int grad, int round_out, void* stream);
+int b200vq_token_embed_fwd(const long long* conds, const long long* codes, const float* Wc, const float* pos_c, const float* Wi,
+                           const float* pos_i, float* x, int B, int Tc, int Ti, int C, int Vc, int Vi, void* stream);
+int b200vq_token_embed_bwd(const long long* conds, const long long* codes, const float* g, float* gWc, float* gpos_c, float* gWi,
+                           float* gpos_i, int B, int Tc, int Ti, int C, int Vc, int Vi, void* stream);
+int b200vq_copy_rows(const float* src, float* dst, int B, int T_src, int T_dst, int off_src, int off_dst, int n, int C,
+                     void* stream);
+int b200vq_decode_attention(const float* qkv, float* cache_k, float* cache_v, float* out, int B, int heads, int hs, int Tmax,
+                            int pos, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Vendor the two reference files the hot path lives in into oracle/_ref/ (git-ignored, NOT gpurun-ignored: it
+"""Vendor the reference files the hot path (and the stage-2 transformer) lives in into oracle/_ref/ (git-ignored, NOT gpurun-ignored: it
 travels to the GPU box with the snapshot like a built .so).
 
     python oracle/build_ref.py            # needs /root/reference (this container); no-op elsewhere
@@ -16,6 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("REFERENCE_ROOT", "/root/reference")
 FILES = ("enhancing/modules/stage1/layers.py", "enhancing/modules/stage1/quantizers.py")
+# copied under another file name (stage 1 also has a layers.py); imports `omegaconf` for a type annotation only -- tests stub it
+RENAMED = {"enhancing/modules/stage2/layers.py": "stage2_layers.py"}
 
 
 def main() -> int:
@@ -25,13 +27,15 @@ def main() -> int:
     dst = os.path.join(HERE, "_ref", "enhancing_ref")
     os.makedirs(dst, exist_ok=True)
     lines = []
-    for f in FILES:
-        out = os.path.join(dst, os.path.basename(f))
+    for f in FILES + tuple(RENAMED):
+        if not os.path.exists(os.path.join(SRC, f)):
+            continue
+        out = os.path.join(dst, RENAMED.get(f, os.path.basename(f)))
         shutil.copyfile(os.path.join(SRC, f), out)
         lines.append(f"{hashlib.sha256(open(out, 'rb').read()).hexdigest()}  {f}")
     with open(os.path.join(dst, "SOURCE.txt"), "w") as fh:
         fh.write("unmodified copies of (sha256, path under the reference repository):\n" + "\n".join(lines) + "\n")
-    print("oracle/_ref/enhancing_ref: " + ", ".join(os.path.basename(f) for f in FILES))
+    print("oracle/_ref/enhancing_ref: " + ", ".join(sorted(x for x in os.listdir(dst) if x.endswith(".py"))))
     return 0
 
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in b200vq.h but not exported by libb200vq.so"
     assert declared == set(etb._lib.EXPORTS), declared ^ set(etb._lib.EXPORTS)
-    assert lib.b200vq_version() == 201
+    assert lib.b200vq_version() == 202
     assert lib.b200vq_arch() == b"sm_100a"
 
 
