@@ -11,7 +11,7 @@ HBM streams (csrc/stage2.cu).
 
 Data path: ``precision`` "parity" -> 3xTF32 GEMMs and attention (fp32-grade); "tf32" and "fp16" -> kind::tf32 GEMMs and
 attention (stage 2 has no fp16-operand path yet).  Limits of the kernels underneath, raised at construction:
-head size ``embed_dim // n_heads`` must be 32 or 64 and ``embed_dim`` <= 2048 (the YAML's 6144 / 16 = 384-wide heads --
+head size ``embed_dim // n_heads`` must be 32 or 64, ``embed_dim`` <= 2048, ``vocab_img_size`` % 32 == 0 (the YAML's 6144 / 16 = 384-wide heads --
 a 10.9 B-parameter model that cannot train under replicated fp32 DDP anyway, SURVEY.md section 8f-3 -- are not covered).
 
 There is no CPU path: CPU tensors raise (use the reference classes on CPU)."""
@@ -268,6 +268,9 @@ class GPT(nn.Module):
     def __init__(self, vocab_cond_size: int, vocab_img_size: int, embed_dim: int, cond_num_tokens: int, img_num_tokens: int,
                  n_heads: int, n_layers: int, mlp_bias: bool = True, attn_bias: bool = True) -> None:
         super().__init__()
+        if vocab_img_size % 32:
+            # the head's weight gradient reads d(logits) as an MN-major tensor-core operand: whole 32-column atoms
+            raise NotImplementedError(f"b200vq stage 2: vocab_img_size must be a multiple of 32 (got {vocab_img_size})")
         self.img_num_tokens = img_num_tokens
         self.vocab_cond_size = vocab_cond_size
         self.tok_emb_cond = nn.Embedding(vocab_cond_size, embed_dim)

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 REF = os.environ.get("B200VQ_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 
-CFG = dict(vocab_cond_size=10, vocab_img_size=48, embed_dim=64, cond_num_tokens=2, img_num_tokens=30, n_heads=2, n_layers=2)
+CFG = dict(vocab_cond_size=10, vocab_img_size=64, embed_dim=64, cond_num_tokens=2, img_num_tokens=30, n_heads=2, n_layers=2)
 
 
 def load_reference_stage2(path=None):
