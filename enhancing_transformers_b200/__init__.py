@@ -9,7 +9,7 @@ import types
 
 from . import _lib, configs, functional, ops  # noqa: F401
 from .functional import get_precision, invalidate_shadows, set_precision  # noqa: F401
-from .layers import (Attention, FeedForward, PreNorm, QuantLinear, Transformer, ViTDecoder, ViTEncoder,  # noqa: F401
+from .layers import (Attention, FeedForward, PosQuantLinear, PreNorm, QuantLinear, Transformer, ViTDecoder, ViTEncoder,  # noqa: F401
                      sincos_table)
 from .parallel import FlatGradients, allreduce_gradients  # noqa: F401
 from .quantizers import BaseQuantizer, GumbelQuantizer, VectorQuantizer  # noqa: F401
@@ -18,7 +18,7 @@ from .stage2 import GPT  # noqa: F401
 
 __version__ = "0.2.0"
 __all__ = ["ViTEncoder", "ViTDecoder", "VectorQuantizer", "GumbelQuantizer", "BaseQuantizer", "Transformer", "Attention", "FeedForward",
-           "PreNorm", "QuantLinear", "GPT", "stage2", "patch", "patch_stage2", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
+           "PreNorm", "QuantLinear", "PosQuantLinear", "fuse_post_quant_pos", "GPT", "stage2", "patch", "patch_stage2", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
            "get_precision", "invalidate_shadows", "allreduce_gradients", "FlatGradients", "ops", "functional", "configs"]
 
 _REF_PKG = "enhancing.modules.stage1"
@@ -61,6 +61,25 @@ def fuse_quant_linears(model):
         lin = getattr(model, name, None)
         if isinstance(lin, nn.Linear) and not isinstance(lin, QuantLinear):
             setattr(model, name, QuantLinear.from_linear(lin))
+    return model
+
+
+def fuse_post_quant_pos(model, enable: bool = True):
+    """Opt-in: make ``model.post_quant`` add the decoder's positional table in its GEMM epilogue and
+    tell ``model.decoder`` to skip its own add -- the [B, N, D] tensor between ``post_quant`` and the decoder's first
+    LayerNorm is written once instead of written, read and written again.  Every path of the unchanged ``ViTVQ``
+    (`decode`, `decode_codes`, `forward`: vitvqgan.py:44-48,68-72,81-90) reaches the decoder through ``post_quant``, which is
+    what makes the pairing safe; calling ``model.decoder`` directly on tokens while this is enabled skips the table.
+    ``enable=False`` restores the separate add."""
+    import torch.nn as nn
+    lin, dec = getattr(model, "post_quant", None), getattr(model, "decoder", None)
+    if not isinstance(lin, nn.Linear) or not isinstance(dec, ViTDecoder):
+        raise TypeError("fuse_post_quant_pos expects a ViTVQ-like module with `post_quant` (nn.Linear) and a b200vq ViTDecoder")
+    if enable:
+        model.post_quant = PosQuantLinear.from_linear(lin, dec)
+    elif isinstance(lin, PosQuantLinear):
+        model.post_quant = QuantLinear.from_linear(lin)
+    dec.pos_added_upstream = bool(enable)
     return model
 
 

@@ -429,6 +429,36 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class LinearPosFn(torch.autograd.Function):
+    """x W^T + b + table[row % n_tok]: ``post_quant`` with the decoder's positional table added in the GEMM epilogue
+    (reference vitvqgan.py:69 followed by layers.py:210) -- SURVEY.md section 8f-1: the [M, D] tensor between the two
+    is never written.  Always 3xTF32, like `QuantLinear`."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, w, b, table):
+        M, K = x.shape
+        N = w.shape[0]
+        n_tok = table.numel() // N
+        y = _mm(x, _W(w, "parity"), M, N, K, "parity", bias=b, res=table.view(n_tok, N), res_row_mod=n_tok)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        M, K = x.shape
+        N = w.shape[0]
+        g = g.contiguous()
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        db = _colsum_of(g) if (ctx.has_bias and need_b) else None
+        dw = _wgrad(g, x, N, K, "parity") if need_w else None
+        dx = _mm(g, _W(w, "parity", True), M, K, N, "parity", b_major=1) if need_x else None
+        return dx, dw, db, None
+
+
 class AttentionCoreFn(torch.autograd.Function):
     """softmax(q k^T * scale) v on the packed qkv matrix (reference layers.py:124-130), stand-alone"""
 

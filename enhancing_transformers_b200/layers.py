@@ -171,6 +171,25 @@ class QuantLinear(nn.Linear):
         return y.view(*x.shape[:-1], self.out_features)
 
 
+class PosQuantLinear(QuantLinear):
+    """``post_quant`` that also adds the decoder's positional table (opt-in through
+    `etb.fuse_post_quant_pos`): one GEMM writes ``post_quant(z) + de_pos_embedding`` and the decoder skips its own add.
+    The table stays the decoder's parameter (same state-dict key); this module only borrows a reference to it."""
+
+    @classmethod
+    def from_linear(cls, lin: nn.Linear, decoder: "ViTDecoder") -> "PosQuantLinear":
+        new = super().from_linear(lin)
+        object.__setattr__(new, "_decoder", decoder)          # not a child module: the decoder is registered once, by ViTVQ
+        return new
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        table = self._decoder.de_pos_embedding
+        tokens = table.shape[1]
+        assert x.shape[-2] == tokens, "post_quant input must carry one row per decoder position"
+        y = Fn.LinearPosFn.apply(_flat2d(x), self.weight, self.bias, table)
+        return y.view(*x.shape[:-1], self.out_features)
+
+
 class _Geometry:
     """image / patch bookkeeping shared by encoder and decoder (reference layers.py:157-166,189-198)"""
 
@@ -225,13 +244,14 @@ class ViTDecoder(nn.Module):
         self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim)
         self.transformer.round_final = True
         self.de_pos_embedding = geo.pos_table(dim)
+        self.pos_added_upstream = False     # set by etb.fuse_post_quant_pos: post_quant's epilogue has already added the table
         deconv = nn.ConvTranspose2d(dim, channels, kernel_size=patch_size, stride=patch_size)
         self.to_pixel = nn.Sequential(nn.Identity(), deconv)             # index 1 keeps the checkpoint key
         _init_like_reference(self)
 
     def forward(self, token: torch.Tensor) -> torch.Tensor:
         batch, tokens, width = token.shape
-        x = Fn.AddPosFn.apply(_flat2d(token), self.de_pos_embedding)
+        x = _flat2d(token) if self.pos_added_upstream else Fn.AddPosFn.apply(_flat2d(token), self.de_pos_embedding)
         x = self.transformer(x.view(batch, tokens, width))
         deconv = self.to_pixel[1]
         height, width_px = self.image_hw

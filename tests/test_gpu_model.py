@@ -119,6 +119,47 @@ def test_against_reference_golden_fwd_bwd(golden_dir, mode):
         assert torch.allclose(q, q2, atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", ["fp16", "parity"])
+def test_post_quant_with_positional_table_in_the_epilogue(golden_dir, mode):
+    """SURVEY.md section 8f-1 (opt-in `etb.fuse_post_quant_pos`): post_quant's GEMM adds de_pos_embedding in its epilogue and
+    the decoder skips its own add.  Same fp32 operations in the same order as the separate path: identical reconstruction,
+    identical decode_codes (vs the reference golden too), identical gradients; state-dict keys unchanged."""
+    etb.set_precision(mode)
+    g = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    img = torch.from_numpy(g["img"]).cuda()
+    gidx = torch.from_numpy(g["idx"]).cuda()
+
+    class Holder(torch.nn.Module):      # the attribute names ViTVQ uses (vitvqgan.py:35-39)
+        def __init__(self, mods):
+            super().__init__()
+            for k, v in mods.items():
+                setattr(self, k, v)
+
+    def grads(mods):
+        loss, rec, idx, _, _ = run(mods, img)
+        loss.backward()
+        return rec.detach(), idx, {f"{m}.{n}": p.grad.clone() for m, mod in mods.items() for n, p in mod.named_parameters() if p.grad is not None}
+
+    plain = build(GOLD_CFG, sd)
+    rec0, idx0, g0 = grads(plain)
+    fused = build(GOLD_CFG, sd)
+    holder = Holder(fused)
+    keys = set(holder.state_dict())
+    etb.fuse_post_quant_pos(holder)
+    assert set(holder.state_dict()) == keys and isinstance(holder.post_quant, etb.PosQuantLinear)
+    fused["post_quant"] = holder.post_quant
+    rec1, idx1, g1 = grads(fused)
+    assert torch.equal(idx0, idx1)
+    assert relmax(rec1, rec0) < 1e-6
+    assert relmax(decode(fused, gidx).cpu(), torch.from_numpy(g["decode_codes"])) < FWD_TOL[mode]
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert ((g1[k] - g0[k]).norm() / g0[k].norm().clamp_min(1e-30)).item() < 1e-5, k
+    etb.fuse_post_quant_pos(holder, False)
+    assert not holder.decoder.pos_added_upstream and type(holder.post_quant) is etb.QuantLinear
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name,B", [("tiny", 3), ("small", 1)])
 def test_against_oracle_shared_state_dict(name, B, mode):
