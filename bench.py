@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--cta-group", type=int, default=int(os.environ.get("B200VQ_CTA_GROUP", "2")))
     ap.add_argument("--ref-batch", type=int, default=4, help="images per CPU step for --impl reference / cpu_baseline")
     ap.add_argument("--ddp", action="store_true", help="torch DistributedDataParallel (overlapped buckets) instead of one flat all-reduce")
+    ap.add_argument("--no-fuse-pos", action="store_true", help="keep post_quant and the decoder's positional add separate")
     ap.add_argument("--extras", default="vq,secondary,eager,cpu",
                     help="comma list of the 1-GPU extra blocks to measure after the timed regions: vq, secondary, eager, cpu ('' = none)")
     args = ap.parse_args()
@@ -312,6 +313,8 @@ def main():
             self.quantizer = etb.VectorQuantizer(**q)
             self.pre_quant = etb.QuantLinear(e["dim"], q["embed_dim"])
             self.post_quant = etb.QuantLinear(q["embed_dim"], d["dim"])
+            if not args.no_fuse_pos:
+                etb.fuse_post_quant_pos(self)      # + de_pos_embedding in post_quant's GEMM epilogue (bit-identical)
 
         def forward(self, x):
             quant, qloss, _ = self.quantizer(self.pre_quant(self.encoder(x)))
@@ -448,12 +451,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp16": "fp16 operands / fp32 accumulate (block GEMMs), tf32 (attention core), fp32 (everything else)",
+            "dtype": {"fp16": "fp16 tensor-core operands / fp32 accumulate (block GEMMs and attention core), 3xtf32 (patch embed, to_pixel, pre/post_quant), fp32 (everything else)",
                       "tf32": "tf32", "parity": "3xtf32 (fp32-grade)"}[precision], "data": "synthetic",
             "config": {"workload": f"imagenet_vitvq_{args.config}.yaml shapes (ViT-VQGAN-{args.config}), synthetic 256x256x3, "
                                    f"fwd+bwd, batch {B}/GPU", "global_batch": world * B, "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "l2_hygiene": "inputs_exceed_l2 (activations >> 126 MB per step)",
-                       "gemm_cta_group": args.cta_group, "precision": precision,
+                       "gemm_cta_group": args.cta_group, "precision": precision, "post_quant_pos_fused": not args.no_fuse_pos,
                        "grad_reduce": ("torch DDP buckets (overlapped)" if args.ddp else "one flat NCCL all-reduce after backward") if world > 1 else "none"},
             "model_tflops_per_gpu": flops_step / (ms_total / args.steps / 1e3) / 1e12,
             "clocks": clocks,
@@ -515,6 +518,37 @@ def main():
                              model_tflops=(4.0 if second else 3.0) * flops_per_image(CONFIGS[cname]) * b / ms / 1e9)
             del m2, st, x
             torch.cuda.empty_cache()
+        # BASELINE config 5 (stage-2 transformer on 1 class token + 32 x 32 codes) at a width the kernels cover
+        import torch.nn.functional as F
+        gcfg = dict(vocab_cond_size=1000, vocab_img_size=8192, embed_dim=1024, cond_num_tokens=1, img_num_tokens=1024, n_heads=16, n_layers=8)
+        torch.manual_seed(0)
+        gpt = etb.GPT(**gcfg).to(dev)
+        gb = 8
+        codes = torch.randint(0, 8192, (gb, 1024), device=dev)
+        conds = torch.randint(0, 1000, (gb, 1), device=dev)
+
+        def gstep():
+            gpt.zero_grad(set_to_none=True)
+            lg = gpt(codes, conds)
+            F.cross_entropy(lg.view(-1, 8192), codes.view(-1)).backward()
+        etb.set_precision("tf32")
+        for _ in range(3):
+            gstep()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            gstep()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 3
+        C, L, T, V = 1024, 8, 1025, 8192
+        sec["stage2_gpt_w1024_L8_B8"] = dict(value=gb * T / ms * 1e3, unit="tokens/s", ms_per_step=ms, batch=gb,
+                                             model_tflops=3.0 * (L * (24 * C * C + 2 * T * C) + 2 * C * V) * gb * T / ms / 1e9,
+                                             note="stage-2 GPT fwd+bwd (cross-entropy), tf32 data path, reduced width (the YAML's 6144 / 384-per-head "
+                                                  "model is not covered by the kernels)")
+        del gpt, codes, conds
+        torch.cuda.empty_cache()
         etb.set_precision(precision)
         sec["note"] = ("3 timed steps after 3 warm-ups each; base_rq4 = BASELINE config 3 (use_residual, num_quantizers=4); large_B32 = the per-GPU "
                        "share of BASELINE config 4 (batch 256 over 8 GPUs); 2fwd_1bwd = the reference training_step shape (vitvqgan.py:101-127); parity_mode = the 3xTF32 data path "
