@@ -172,12 +172,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int inner = p.heads * DH;
-  const int T = p.kv_tiles;
+  // key tiles an item visits: all of them, or -- under the stage-2 mask -- those up to the last key any of its rows sees
+  auto tiles_of = [&](int w) -> int {
+    if (p.cond < 0) return p.kv_tiles;
+    const int last = max(min(p.N - 1, (w % p.q_tiles) * 128 + 127), p.cond - 1);
+    return min(p.kv_tiles, last / 128 + 1);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
     uint32_t kv_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int T = tiles_of(w);
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -214,6 +220,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint64_t kd0 = make_smem_desc(smem_u32(Ks), 16, 1024, kLayoutSw128);
     uint32_t s_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int T = tiles_of(w);
       mbar_wait(q_full, item_it & 1);
       for (int j = 0; j < T; ++j, ++s_it) {
         const int s = s_it & 1;
@@ -241,6 +248,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const uint64_t vd0 = make_smem_desc(smem_u32(Vs), KBLK_BYTES, 512, kLayoutSw128Base32);
     uint32_t pv_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const int T = tiles_of(w);
       for (int j = 0; j < T; ++j, ++pv_it) {
         const int s = pv_it & 1;
         const uint32_t ph = (pv_it >> 1) & 1;
@@ -277,6 +285,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const int T = tiles_of(w);
       const int qt = w % p.q_tiles;
       const int bh = w / p.q_tiles;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -818,11 +827,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int inner = p.heads * DH;
-  const int NS = p.sub64;
+  // 64-key sub-tiles an item visits (stage-2 mask: up to the last key any of its 128 rows sees)
+  auto subs_of = [&](int w) -> int {
+    if (p.cond < 0) return p.sub64;
+    const int last = max(min(p.N - 1, (w % p.tiles128) * 128 + 127), p.cond - 1);
+    return min(p.sub64, last / 64 + 1);
+  };
 
   if (warp == 0) {
     uint32_t sub_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int NS = subs_of(w);
       const int qt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -866,6 +881,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
     const uint64_t kkd0 = make_smem_desc(smem_u32(St), 16, 1024, kLayoutSw128);
     uint32_t sd_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int NS = subs_of(w);
       mbar_wait(q_full, item_it & 1);
       for (int i = 0; i < NS; ++i, ++sd_it) {
         const int s = sd_it & 1;
@@ -899,6 +915,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
     const uint64_t kmd0 = make_smem_desc(smem_u32(St + 2 * T64), KBLK64, 512, kLayoutSw128Base32);
     uint32_t dq_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int NS = subs_of(w);
       for (int i = 0; i < NS; ++i, ++dq_it) {
         const int s = dq_it & 1;
         const uint32_t ph = (dq_it >> 1) & 1;
@@ -927,6 +944,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_c
     const float c = p.scale * kLog2eF;
     uint32_t t_it = 0, item_it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_it) {
+      const int NS = subs_of(w);
       const int qt = w % p.tiles128;
       const int bh = w / p.tiles128;
       const int h = bh % p.heads, b = bh / p.heads;
