@@ -9,9 +9,10 @@ the vocabulary head on the tcgen05 GEMMs, the masked attention core on the tcgen
 causal + visible-prefix mask folded in, time-shift mixing, squared ReLU, embeddings and the logits window as
 HBM streams (csrc/stage2.cu).
 
-Data path: ``precision`` "parity" -> 3xTF32 GEMMs and attention (fp32-grade); "tf32" and "fp16" -> kind::tf32 GEMMs and
-attention (stage 2 has no fp16-operand path yet).  Limits of the kernels underneath, raised at construction:
-head size ``embed_dim // n_heads`` must be 32 or 64, ``embed_dim`` <= 2048, ``vocab_img_size`` % 32 == 0 (the YAML's 6144 / 16 = 384-wide heads --
+Data path (``etb.set_precision``): "fp16" (default) -> the Linear layers on kind::f16 GEMMs (fp16 operands, fp32 accumulate and
+output, per-call power-of-two gradient scaling chosen on the device), attention core on kind::tf32; "tf32" -> everything
+kind::tf32; "parity" -> 3xTF32 GEMMs and attention (fp32-grade).  Limits of the kernels underneath, raised at construction:
+head size ``embed_dim // n_heads`` must be 32 or 64, ``embed_dim`` <= 2048, ``vocab_img_size`` % 64 == 0 (the YAML's 6144 / 16 = 384-wide heads --
 a 10.9 B-parameter model that cannot train under replicated fp32 DDP anyway, SURVEY.md section 8f-3 -- are not covered).
 
 There is no CPU path: CPU tensors raise (use the reference classes on CPU)."""
@@ -33,7 +34,17 @@ _fwd, _bwd = Fn._fwd, Fn._bwd
 
 
 def _mode() -> str:
+    """data path of the attention core and of everything that is not a Linear: "parity" (3xTF32) or "tf32" """
     return "parity" if Fn.get_precision() == "parity" else "tf32"
+
+
+def _linear(x: Tensor, w: Tensor, b: Optional[Tensor], res: Optional[Tensor] = None) -> Tensor:
+    """x W^T + b (+ res) on the data path `etb.set_precision` selects: fp16 tensor-core operands (default), tf32, or 3xTF32"""
+    if Fn.get_precision() == "fp16":
+        return LinearF16Fn.apply(x, w, b, res)
+    if res is None:
+        return Fn.LinearFn.apply(x, w, b, 0, False)
+    return LinearResFn.apply(x, w, b, res)
 
 
 class TokenEmbedFn(torch.autograd.Function):
@@ -120,6 +131,39 @@ class LinearResFn(torch.autograd.Function):
         return dx, dw, db, (g if need_res else None)
 
 
+class LinearF16Fn(torch.autograd.Function):
+    """x W^T + b (+ res) with fp16 tensor-core operands and fp32 accumulation / output (kind::f16: tf32's 11-bit significand
+    at twice the tensor rate and half the operand bytes -- DESIGN.md section 2).  Self-contained gradient scaling: backward
+    picks the power of two S that puts max|g| at 2^6 on the device (`ops.grad_scale`, no host sync), feeds fp16(g S) to the
+    dgrad / wgrad GEMMs and multiplies their fp32 results by 1/S in the epilogue (exact)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, w, b, res):
+        M, K = x.shape
+        N = w.shape[0]
+        x16 = ops.to_half(x)
+        y = ops.gemm(x16, Fn.weight_shadow(w, "f16"), M, N, K, bias=b, res=res, cta_group=Fn.GEMM_CTA_GROUP)
+        ctx.save_for_backward(x16, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        x16, w = ctx.saved_tensors
+        M, K = x16.shape
+        N = w.shape[0]
+        g = g.contiguous()
+        need_x, need_w, need_b, need_res = ctx.needs_input_grad[:4]
+        sc = ops.grad_scale(g)
+        gh = ops.to_half(g, sc[0:1])
+        db = ops.colsum(g) if (ctx.has_bias and need_b) else None
+        dw = Fn._wgrad(gh, x16, N, K, inv_scale=sc[1:2]) if need_w else None
+        dx = ops.gemm(gh, Fn.weight_shadow(w, "f16", True), M, K, N, b_major=1, alpha=sc[1:2], cta_group=Fn.GEMM_CTA_GROUP) if need_x else None
+        return dx, dw, db, (g if need_res else None)
+
+
 class CausalAttentionFn(torch.autograd.Function):
     """softmax(mask(q k^T / sqrt(hs))) v on the packed qkv matrix (reference stage2/layers.py:76-89): the mask is
     tril with the cond_len x cond_len prefix block fully visible (:43-48)."""
@@ -203,12 +247,10 @@ class MultiHeadSelfAttention(nn.Module):
         C = flat.shape[-1]
         mixed = TimeMixFn.apply(flat, self.time_mix, T)
         w, b = self.packed_qkv()
-        qkv = Fn.LinearFn.apply(mixed, w, b, 0, False)
+        qkv = _linear(mixed, w, b)
         cond = min(self.cond_len, T) if self.use_mask else T      # no mask == every key visible == a prefix of T tokens
         o = CausalAttentionFn.apply(qkv, B, T, self.n_heads, C // self.n_heads, cond)
-        if res is None:
-            return Fn.LinearFn.apply(o, self.proj.weight, self.proj.bias, 0, False)
-        return LinearResFn.apply(o, self.proj.weight, self.proj.bias, res)
+        return _linear(o, self.proj.weight, self.proj.bias, res)
 
     def forward(self, x: Tensor, use_cache: bool = False, layer_past=None):
         if use_cache or layer_past is not None:
@@ -229,10 +271,8 @@ class FFN(nn.Module):
     def core(self, flat: Tensor, res: Optional[Tensor] = None) -> Tensor:
         # the squared ReLU stays a stream kernel of its own: folded into the GEMM epilogue (measured, same box) it cost the
         # stage-1 GEMMs 2 % through the larger epilogue code, for a gain that only stage 2 sees
-        hidden = SqReluFn.apply(Fn.LinearFn.apply(flat, self.p0.weight, self.p0.bias, 0, False))
-        if res is None:
-            return Fn.LinearFn.apply(hidden, self.p1.weight, self.p1.bias, 0, False)
-        return LinearResFn.apply(hidden, self.p1.weight, self.p1.bias, res)
+        hidden = SqReluFn.apply(_linear(flat, self.p0.weight, self.p0.bias))
+        return _linear(hidden, self.p1.weight, self.p1.bias, res)
 
     def forward(self, x: Tensor) -> Tensor:
         return self.core(_flat2d(x)).view(*x.shape[:-1], -1)
@@ -270,9 +310,9 @@ class GPT(nn.Module):
     def __init__(self, vocab_cond_size: int, vocab_img_size: int, embed_dim: int, cond_num_tokens: int, img_num_tokens: int,
                  n_heads: int, n_layers: int, mlp_bias: bool = True, attn_bias: bool = True) -> None:
         super().__init__()
-        if vocab_img_size % 32:
-            # the head's weight gradient reads d(logits) as an MN-major tensor-core operand: whole 32-column atoms
-            raise NotImplementedError(f"b200vq stage 2: vocab_img_size must be a multiple of 32 (got {vocab_img_size})")
+        if vocab_img_size % 64:
+            # the head's weight gradient reads d(logits) as an MN-major tensor-core operand: whole 64-column (fp16) atoms
+            raise NotImplementedError(f"b200vq stage 2: vocab_img_size must be a multiple of 64 (got {vocab_img_size})")
         self.img_num_tokens = img_num_tokens
         self.vocab_cond_size = vocab_cond_size
         self.tok_emb_cond = nn.Embedding(vocab_cond_size, embed_dim)
@@ -309,7 +349,7 @@ class GPT(nn.Module):
             x = block.run(x, B, T)
         x = Fn.LayerNormFn.apply(x, self.layer_norm.weight, self.layer_norm.bias, False)
         x = RowWindowFn.apply(x, B, T, Tc - 1, Ti)                    # positions cond-1 .. T-2 predict the Ti codes
-        logits = Fn.LinearFn.apply(x, self.head.weight, None, 0, False)
+        logits = _linear(x, self.head.weight, None)
         return logits.view(B, Ti, -1)
 
     # ------------------------------------------------------------------------------------------ sampling
@@ -370,7 +410,7 @@ class GPT(nn.Module):
                 h = Fn.LayerNormFn.apply(x, block.ln1.weight, block.ln1.bias, False)
                 mixed = ops.time_mix_fwd(h, att.time_mix.view(-1), Tc)
                 w, b = att.packed_qkv()
-                qkv = Fn.LinearFn.apply(mixed, w, b, 0, False)
+                qkv = _linear(mixed, w, b)
                 ck = torch.zeros(B, ctx, C, device=dev)
                 cv = torch.zeros(B, ctx, C, device=dev)
                 q3 = qkv.view(B, Tc, 3, C)
@@ -379,7 +419,7 @@ class GPT(nn.Module):
                 past["k"].append(ck)
                 past["v"].append(cv)
                 o = CausalAttentionFn.apply(qkv, B, Tc, heads, hs, Tc)      # the condition prefix sees itself fully (:83-85 with T == cond_len)
-                x = LinearResFn.apply(o, att.proj.weight, att.proj.bias, x)
+                x = _linear(o, att.proj.weight, att.proj.bias, x)
                 x = block.mlp.core(Fn.LayerNormFn.apply(x, block.ln2.weight, block.ln2.bias, False), res=x)
             x = Fn.LayerNormFn.apply(x, self.layer_norm.weight, self.layer_norm.bias, False)
             x = ops.copy_rows(x, B, Tc, 1, Tc - 1, 0, 1)
@@ -396,11 +436,11 @@ class GPT(nn.Module):
                 h = Fn.LayerNormFn.apply(x, block.ln1.weight, block.ln1.bias, False)
                 mixed = ops.time_mix_fwd(h, att.time_mix.view(-1), 1)
                 w, b = att.packed_qkv()
-                qkv = Fn.LinearFn.apply(mixed, w, b, 0, False)
+                qkv = _linear(mixed, w, b)
                 o = ops.decode_attention(qkv, past["k"][li], past["v"][li], heads, hs, pos, scale)
-                x = LinearResFn.apply(o, att.proj.weight, att.proj.bias, x)
+                x = _linear(o, att.proj.weight, att.proj.bias, x)
                 x = block.mlp.core(Fn.LayerNormFn.apply(x, block.ln2.weight, block.ln2.bias, False), res=x)
             past["len"] = pos + 1
             x = Fn.LayerNormFn.apply(x, self.layer_norm.weight, self.layer_norm.bias, False)
-        logits = Fn.LinearFn.apply(x, self.head.weight, None, 0, False)
+        logits = _linear(x, self.head.weight, None)
         return logits, past

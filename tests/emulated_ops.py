@@ -15,7 +15,7 @@ def _mat(t, major, rows, k_total):
 
 def gemm(a, b, M, N, K, *, a_major=0, b_major=0, lda=None, ldb=None, out=None, bias=None, res=None, res_row_mod=0, aux=None,
          act=0, round_out=False, splits=1, cta_group=1, bn=0, want_colsum=False, a_lo=None, b_lo=None, out_half=False, alpha=None):
-    assert not out_half and out is None
+    assert out is None
     outs = []
     for z in range(splits):
         A = _mat(a, a_major, M, K * splits)[:, z * K:(z + 1) * K]
@@ -32,7 +32,7 @@ def gemm(a, b, M, N, K, *, a_major=0, b_major=0, lda=None, ldb=None, out=None, b
         if res is not None:
             r = res.double().view(-1, N)
             c = c + (r[torch.arange(M) % res_row_mod] if res_row_mod else r)
-        outs.append(c.float())
+        outs.append(c.half() if out_half else c.float())
     c = outs[0] if splits == 1 else torch.stack(outs)
     return (c, c.sum(0)) if want_colsum else c
 
@@ -48,6 +48,16 @@ def round_tf32(x, out=None):
 
 def split_tf32_lo(x):
     return torch.zeros_like(x)
+
+
+def to_half(x, scale=None):
+    return (x if scale is None else x * scale).clamp(-65504, 65504).half()
+
+
+def grad_scale(g, target_log2=6):
+    m = g.abs().max().clamp_min(1e-30)
+    S = torch.exp2(target_log2 - torch.ceil(torch.log2(m)))
+    return torch.stack([S, 1 / S]).float()
 
 
 def layernorm_fwd(x, gamma, beta, round_out, out_half=False):
@@ -160,7 +170,7 @@ def launch_count():
     return _COUNT[0]
 
 
-NAMES = ("gemm", "splitk_reduce", "round_tf32", "split_tf32_lo", "layernorm_fwd", "layernorm_bwd", "colsum", "attention_causal_fwd",
+NAMES = ("gemm", "splitk_reduce", "round_tf32", "split_tf32_lo", "to_half", "grad_scale", "layernorm_fwd", "layernorm_bwd", "colsum", "attention_causal_fwd",
          "attention_causal_bwd", "time_mix_fwd", "time_mix_bwd", "sqrelu", "token_embed_fwd", "token_embed_bwd", "copy_rows",
          "decode_attention", "launch_count")
 
@@ -172,4 +182,5 @@ def install(monkeypatch):
     # the weight-shadow makers captured the real wrappers at import time
     monkeypatch.setitem(functional._SHADOW_MAKERS, "tf32", round_tf32)
     monkeypatch.setitem(functional._SHADOW_MAKERS, "lo", split_tf32_lo)
+    monkeypatch.setitem(functional._SHADOW_MAKERS, "f16", to_half)
     monkeypatch.setattr(ops, "pick_splits", lambda *a, **k: 1)

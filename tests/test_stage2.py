@@ -111,10 +111,10 @@ def test_gpt_module_tree_and_state_dict_match_reference(golden_dir):
 def test_gpt_rejects_geometries_without_a_kernel():
     import enhancing_transformers_b200 as etb
     with pytest.raises(NotImplementedError, match="head size"):
-        etb.GPT(vocab_cond_size=10, vocab_img_size=32, embed_dim=6144, cond_num_tokens=1, img_num_tokens=4, n_heads=16, n_layers=1)
+        etb.GPT(vocab_cond_size=10, vocab_img_size=64, embed_dim=6144, cond_num_tokens=1, img_num_tokens=4, n_heads=16, n_layers=1)
     with pytest.raises(AssertionError):
-        etb.GPT(vocab_cond_size=10, vocab_img_size=32, embed_dim=100, cond_num_tokens=1, img_num_tokens=4, n_heads=3, n_layers=1)
-    model = etb.GPT(vocab_cond_size=10, vocab_img_size=32, embed_dim=64, cond_num_tokens=1, img_num_tokens=4, n_heads=2, n_layers=1)
+        etb.GPT(vocab_cond_size=10, vocab_img_size=64, embed_dim=100, cond_num_tokens=1, img_num_tokens=4, n_heads=3, n_layers=1)
+    model = etb.GPT(vocab_cond_size=10, vocab_img_size=64, embed_dim=64, cond_num_tokens=1, img_num_tokens=4, n_heads=2, n_layers=1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         model(torch.zeros(2, 4, dtype=torch.int64), torch.zeros(2, 1, dtype=torch.int64))
 
@@ -127,7 +127,7 @@ def test_patch_stage2_rebinds_the_reference_names():
     assert fake.GPT is etb.GPT and fake.Block is etb.stage2.Block and fake.MultiHeadSelfAttention is etb.stage2.MultiHeadSelfAttention
 
 
-@pytest.mark.parametrize("mode", ["parity", "tf32"])
+@pytest.mark.parametrize("mode", ["parity", "tf32", "fp16"])
 def test_gpt_host_logic_with_emulated_kernels(golden_dir, monkeypatch, mode):
     """stage2.py's autograd wiring / packed-qkv layout / row windows / KV-cache bookkeeping, with every C-ABI call replaced
     by a torch stand-in that follows the contract in include/b200vq.h (tests/emulated_ops.py): the host side alone must
@@ -145,9 +145,15 @@ def test_gpt_host_logic_with_emulated_kernels(golden_dir, monkeypatch, mode):
         logits = model(codes, conds)
         loss = F.cross_entropy(logits.view(-1, logits.shape[-1]), codes.view(-1))
         loss.backward()
-        torch.testing.assert_close(logits.detach(), torch.from_numpy(g["logits"]), rtol=1e-4, atol=1e-5)
+        half = mode == "fp16"       # the stand-ins really round operands to fp16 there (the scaling logic depends on the dtype)
+        assert _rel(logits.detach(), torch.from_numpy(g["logits"])) < (3e-3 if half else 1e-5)
         for name, p in model.named_parameters():
-            torch.testing.assert_close(p.grad, torch.from_numpy(g["grad." + name]), rtol=1e-3, atol=1e-6, msg=lambda m: f"{name}: {m}")
+            want = torch.from_numpy(g["grad." + name])
+            if name.endswith("attn.key.bias"):
+                assert p.grad.abs().max().item() < 1e-4
+                continue
+            e = ((p.grad - want).norm() / want.norm().clamp_min(1e-12)).item()
+            assert e < (1e-2 if half else 1e-4), (name, e)
         model.eval()
         s_codes = torch.from_numpy(g["sample_codes"])
         past, got = None, []
@@ -155,10 +161,11 @@ def test_gpt_host_logic_with_emulated_kernels(golden_dir, monkeypatch, mode):
             lg, past = model.sample_step(None if i == 0 else s_codes[:, i - 1:i], conds,
                                          None if i == 0 else model.pos_emb_code[:, i - 1:i, :], False, past)
             got.append(lg)
-        torch.testing.assert_close(torch.stack(got, 1), torch.from_numpy(g["sample_logits"]), rtol=1e-4, atol=1e-5)
+        assert _rel(torch.stack(got, 1), torch.from_numpy(g["sample_logits"])) < (3e-3 if half else 1e-5)
         torch.manual_seed(99)                                   # the seed the golden's sampler ran under, same CPU RNG stream
         s_logits, drawn = model.sample(conds, use_fp16=False)
-        assert torch.equal(drawn, s_codes)
+        if not half:
+            assert torch.equal(drawn, s_codes)
     finally:
         etb.set_precision(prev)
 
@@ -298,7 +305,7 @@ def _gpt_on_gpu(sd, cfg):
 
 
 @gpu
-@pytest.mark.parametrize("mode,tol_logit,tol_grad", [("parity", 1e-4, 1e-3), ("tf32", 1e-2, 3e-2)])
+@pytest.mark.parametrize("mode,tol_logit,tol_grad", [("parity", 1e-4, 1e-3), ("tf32", 1e-2, 3e-2), ("fp16", 1e-2, 3e-2)])
 def test_gpt_matches_reference_golden(golden_dir, mode, tol_logit, tol_grad):
     """forward logits, cross-entropy loss and every parameter gradient of the reference's own GPT (tiny config);
     north_star tolerance for logits: 1e-3 relative -- the parity data path is asserted at 1e-4"""
@@ -365,7 +372,7 @@ def test_gpt_sampling_steps_match_reference_golden(golden_dir):
 
 
 @gpu
-@pytest.mark.parametrize("mode,tol", [("parity", 1e-4), ("tf32", 1e-2)])
+@pytest.mark.parametrize("mode,tol", [("parity", 1e-4), ("tf32", 1e-2), ("fp16", 1e-2)])
 def test_gpt_base_shaped_sequence_vs_fp64_oracle(mode, tol):
     """config 5's sequence geometry (1 class token + 32 x 32 codes = 1025 positions, 8192-entry vocabulary) at a width the
     kernels cover (embed_dim 256, 64-wide heads), against the oracle evaluated in fp64 on the GPU"""
