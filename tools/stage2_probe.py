@@ -30,7 +30,7 @@ def main():
     codes = torch.randint(0, 8192, (B, 1024), device="cuda")
     conds = torch.randint(0, 1000, (B, 1), device="cuda")
     out = {"config": cfg, "batch": B}
-    for mode in ("tf32", "parity"):
+    for mode in ("fp16", "tf32", "parity"):
         etb.set_precision(mode)
         def step():
             model.zero_grad(set_to_none=True)
@@ -42,7 +42,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        iters = 5 if mode == "tf32" else 2
+        iters = 2 if mode == "parity" else 5
         for _ in range(iters):
             step()
         e1.record()
