@@ -182,3 +182,27 @@ def test_unchanged_lightning_module_constructs_with_patched_classes(monkeypatch)
     plain = torch.nn.Linear(64, 32)
     fused = etb.QuantLinear.from_linear(plain)
     assert fused.weight is plain.weight and fused.bias is plain.bias and isinstance(fused, torch.nn.Linear)
+
+
+def test_fuse_post_quant_pos_keeps_the_checkpoint_abi():
+    """post_quant borrows the decoder's positional table without registering it a second
+    time -- same state-dict keys, same Parameter objects, reversible"""
+    import torch
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.decoder = etb.ViTDecoder(32, 8, dim=64, depth=1, heads=2, mlp_dim=128, dim_head=32)
+            self.post_quant = torch.nn.Linear(32, 64)
+
+    m = Holder()
+    keys, params = set(m.state_dict()), {id(p) for p in m.parameters()}
+    w = m.post_quant.weight
+    etb.fuse_post_quant_pos(m)
+    assert isinstance(m.post_quant, etb.PosQuantLinear) and m.post_quant.weight is w and m.decoder.pos_added_upstream
+    assert set(m.state_dict()) == keys and {id(p) for p in m.parameters()} == params
+    m.load_state_dict(m.state_dict(), strict=True)
+    etb.fuse_post_quant_pos(m, False)
+    assert type(m.post_quant) is etb.QuantLinear and m.post_quant.weight is w and not m.decoder.pos_added_upstream
+    with pytest.raises(TypeError):
+        etb.fuse_post_quant_pos(torch.nn.Linear(2, 2))
