@@ -250,8 +250,16 @@ def test_baseline_config_parity_vs_fp64_oracle(name, B, mode):
     assert (errs["tokens_differing"] <= max(2, ntok // 5000)) if not fast else (agree >= 1.0 - 0.008 * depth), errs
     audit_flipped_codes(idx, idx64, z.detach(), z64.detach(), E)
     # decoder fed the ORACLE'S codes: the reconstruction tolerance proper
-    errs["dec_on_oracle_codes"] = relmax(decode(mods, idx64), rec64.detach())
+    dec = decode(mods, idx64)
+    errs["dec_on_oracle_codes"] = relmax(dec, rec64.detach())
     assert errs["dec_on_oracle_codes"] < tol, errs
+    # the same comparison under two stricter readings of "relative", reported next to it:
+    # relative l2 over the image, and the 99.9th percentile of the per-pixel error relative to the per-image RMS
+    diff = (dec.double() - rec64.detach())
+    errs["dec_rel_l2"] = (diff.norm() / rec64.detach().norm()).item()
+    rms = rec64.detach().pow(2).mean(dim=(1, 2, 3), keepdim=True).sqrt()
+    errs["dec_p999_over_rms"] = torch.quantile((diff.abs() / rms).flatten()[:4_000_000].float(), 0.999).item()
+    assert errs["dec_rel_l2"] < tol, errs
     if agree == 1.0:
         assert relmax(rec, rec64.detach()) < tol and abs(loss.item() - loss64.item()) < tol * abs(loss64.item()), errs
     else:
