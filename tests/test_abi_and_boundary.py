@@ -206,3 +206,57 @@ def test_fuse_post_quant_pos_keeps_the_checkpoint_abi():
     assert type(m.post_quant) is etb.QuantLinear and m.post_quant.weight is w and not m.decoder.pos_added_upstream
     with pytest.raises(TypeError):
         etb.fuse_post_quant_pos(torch.nn.Linear(2, 2))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_unchanged_cond_transformer_constructs_with_patch_stage2(monkeypatch):
+    """CondTransformer from the reference's stage2/transformer.py, unedited: after `etb.patch_stage2` its YAML-style
+    `transformer.target: enhancing.modules.stage2.layers.GPT` resolves (by the reference's own get_obj_from_str logic,
+    utils/general.py:29-41) to this package's GPT; `configure_optimizers` (transformer.py:131-166) sorts its parameters
+    into decay / no-decay sets without leftovers."""
+    import importlib
+    import importlib.util
+    import sys
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, m)
+        return m
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    def initialize_from_config(config):                      # utils/general.py:29-41, verbatim semantics
+        module, cls = config["target"].rsplit(".", 1)
+        return getattr(importlib.import_module(module), cls)(**config.get("params", dict()))
+
+    stub("omegaconf", OmegaConf=AttrDict)
+    stub("pytorch_lightning", LightningModule=torch.nn.Module)
+    for pkg in ("enhancing", "enhancing.modules", "enhancing.modules.stage2", "enhancing.utils"):
+        stub(pkg).__path__ = []
+    stub("enhancing.utils.general", initialize_from_config=initialize_from_config)
+    stub("frozen_stub", Frozen=lambda **kw: torch.nn.Linear(2, 2))    # stands in for the cond / stage-1 models
+    s2 = os.path.join(REF, "enhancing", "modules", "stage2")
+    for name in ("layers", "transformer"):
+        spec = importlib.util.spec_from_file_location(f"enhancing.modules.stage2.{name}", os.path.join(s2, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        monkeypatch.setitem(sys.modules, spec.name, mod)
+        spec.loader.exec_module(mod)
+        if name == "layers":
+            ref_gpt = mod.GPT
+            etb.patch_stage2(mod)                               # before transformer.py does `from .layers import *`
+            assert mod.GPT is etb.GPT and mod.GPT is not ref_gpt
+    tr = sys.modules["enhancing.modules.stage2.transformer"]
+    gpt_cfg = AttrDict(target="enhancing.modules.stage2.layers.GPT",
+                       params=dict(vocab_cond_size=10, vocab_img_size=64, embed_dim=64, cond_num_tokens=1, img_num_tokens=16, n_heads=2, n_layers=2))
+    frozen = AttrDict(target="frozen_stub.Frozen", params={})
+    model = tr.CondTransformer(cond_key="class", cond=frozen, stage1=frozen, transformer=gpt_cfg)
+    assert isinstance(model.transformer, etb.GPT)
+    model.learning_rate = 1e-4
+    (optimizer,), _ = model.configure_optimizers()
+    n_opt = sum(len(g["params"]) for g in optimizer.param_groups)
+    assert n_opt == len(list(model.transformer.parameters()))
+    decay = {id(p) for p in optimizer.param_groups[0]["params"]}
+    assert id(model.transformer.head.weight) in decay and id(model.transformer.blocks[0].attn.time_mix) not in decay
