@@ -18,7 +18,7 @@ from .stage2 import GPT  # noqa: F401
 
 __version__ = "0.2.0"
 __all__ = ["ViTEncoder", "ViTDecoder", "VectorQuantizer", "GumbelQuantizer", "BaseQuantizer", "Transformer", "Attention", "FeedForward",
-           "PreNorm", "QuantLinear", "PosQuantLinear", "fuse_post_quant_pos", "GPT", "stage2", "patch", "patch_stage2", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
+           "PreNorm", "QuantLinear", "PosQuantLinear", "fuse_post_quant_pos", "detach_discriminator_forward", "GPT", "stage2", "patch", "patch_stage2", "install_as_reference_modules", "fuse_quant_linears", "set_precision",
            "get_precision", "invalidate_shadows", "allreduce_gradients", "FlatGradients", "ops", "functional", "configs"]
 
 _REF_PKG = "enhancing.modules.stage1"
@@ -81,6 +81,36 @@ def fuse_post_quant_pos(model, enable: bool = True):
         model.post_quant = QuantLinear.from_linear(lin)
     dec.pos_added_upstream = bool(enable)
     return model
+
+
+def detach_discriminator_forward(vitvq_cls):
+    """Opt-in: the reference's ``ViTVQ.training_step`` runs the whole autoencoder a second time for
+    the discriminator update (``optimizer_idx == 1``, vitvqgan.py:100-127) although the loss only ever reads
+    ``reconstructions.detach()`` there (losses/vqperceptual.py:154-158).  This wraps ``training_step`` / ``forward`` of the
+    class -- at run time, the file is not edited -- so that this second forward runs under ``torch.no_grad()``: identical
+    values (same weights, same kernels), no activations saved, no autograd graph built.  Returns the class."""
+    import torch
+    if getattr(vitvq_cls.training_step, "_b200vq_wrapped", False):
+        return vitvq_cls
+    orig_step, orig_forward = vitvq_cls.training_step, vitvq_cls.forward
+
+    def training_step(self, batch, batch_idx, optimizer_idx=0):
+        self._b200vq_detached_forward = optimizer_idx == 1
+        try:
+            return orig_step(self, batch, batch_idx, optimizer_idx)
+        finally:
+            self._b200vq_detached_forward = False
+
+    def forward(self, x):
+        if getattr(self, "_b200vq_detached_forward", False):
+            with torch.no_grad():
+                return orig_forward(self, x)
+        return orig_forward(self, x)
+
+    training_step._b200vq_wrapped = True
+    training_step.__wrapped__, forward.__wrapped__ = orig_step, orig_forward
+    vitvq_cls.training_step, vitvq_cls.forward = training_step, forward
+    return vitvq_cls
 
 
 def _wrap_vitvq_init(vitvqgan_module):

@@ -182,6 +182,36 @@ def test_unchanged_lightning_module_constructs_with_patched_classes(monkeypatch)
     plain = torch.nn.Linear(64, 32)
     fused = etb.QuantLinear.from_linear(plain)
     assert fused.weight is plain.weight and fused.bias is plain.bias and isinstance(fused, torch.nn.Linear)
+    # opt-in: the discriminator step's forward (optimizer_idx == 1, vitvqgan.py:116-127) runs without an autograd graph
+    seen = []
+
+    class Probe(torch.nn.Module):                                # stands in for VQLPIPSWithDiscriminator
+        def forward(self, qloss, x, xrec, optimizer_idx, *a, **k):
+            seen.append((optimizer_idx, xrec.requires_grad, torch.is_grad_enabled()))
+            key = "train/total_loss" if optimizer_idx == 0 else "train/disc_loss"
+            return xrec.sum() * 0 + 1.0, {key: torch.tensor(1.0)}
+
+
+    class Tiny(mod.ViTVQ):                                       # no GPU here: swap the heavy parts for CPU stand-ins
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.image_key, self.loss = "image", Probe()
+            self.lin = torch.nn.Linear(4, 4)
+            self.decoder = types.SimpleNamespace(get_last_layer=lambda: self.lin.weight)
+            self.global_step = 0
+        encode = lambda self, x: (self.lin(x), x.sum() * 0)
+        decode = lambda self, q: q
+        log = log_dict = lambda self, *a, **k: None
+
+    etb.detach_discriminator_forward(Tiny)
+    etb.detach_discriminator_forward(Tiny)                       # idempotent
+    m = Tiny()
+    batch = {"image": torch.randn(2, 4, 4, 4)}
+    m.training_step(batch, 0, 0)
+    m.training_step(batch, 0, 1)
+    m.training_step(batch, 0, 0)
+    assert seen == [(0, True, True), (1, False, True), (0, True, True)], seen
+    assert mod.ViTVQ.forward is not Tiny.forward                  # only the class it was asked to wrap
 
 
 def test_fuse_post_quant_pos_keeps_the_checkpoint_abi():
