@@ -466,7 +466,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 7.533e8 if (args.config == "base" and B == 128 and precision == "fp16") else None,
+                         "traffic": 7.544e8 if (args.config == "base" and B == 128 and precision == "fp16") else None,
                          "traffic_note": "dram read+write bytes of one to_qkv launch (M=131072 N=2304 K=768, fp16 in/out) from profiles/r02_ncu_gemm_f16.txt "
                                          "(ncu --set full); algorithmic bytes of that launch: 8.09e8 (A 201 MB + B 3.5 MB + C 604 MB); tensor pipe 86 % "
                                          "active there, 90 % on the K=3072 net.2 launch",
