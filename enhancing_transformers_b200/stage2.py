@@ -19,7 +19,7 @@ There is no CPU path: CPU tensors raise (use the reference classes on CPU)."""
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn

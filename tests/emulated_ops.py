@@ -3,7 +3,6 @@ following the contracts written in include/b200vq.h.  `install(monkeypatch)` swa
 stage2.py (autograd wiring, argument order, packed-qkv layout, row windows, KV-cache bookkeeping) can be checked against the
 reference golden on a machine without a GPU.  The product never imports this file and has no CPU path; the kernels
 themselves are checked on the GPU (tests/test_stage2.py -m gpu)."""
-import math
 
 import torch
 

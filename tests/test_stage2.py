@@ -18,7 +18,6 @@ import torch.nn.functional as F
 from oracle import gpt_oracle as G
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HAS_GPU = torch.cuda.is_available()
 gpu = pytest.mark.gpu
 
 
