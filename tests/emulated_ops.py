@@ -1,8 +1,8 @@
-"""TEST INFRASTRUCTURE ONLY: torch-CPU stand-ins for the `enhancing_transformers_b200.ops` wrappers the stage-2 modules call,
+"""TEST INFRASTRUCTURE ONLY: torch-CPU stand-ins for the `enhancing_transformers_b200.ops` wrappers the modules call,
 following the contracts written in include/b200vq.h.  `install(monkeypatch)` swaps them in so that the *host logic* of
-stage2.py (autograd wiring, argument order, packed-qkv layout, row windows, KV-cache bookkeeping) can be checked against the
-reference golden on a machine without a GPU.  The product never imports this file and has no CPU path; the kernels
-themselves are checked on the GPU (tests/test_stage2.py -m gpu)."""
+functional.py / layers.py / quantizers.py / stage2.py (autograd wiring, argument order, operand majors, gradient scaling,
+packed-qkv layout, row windows, KV-cache bookkeeping) can be checked against the reference goldens on a machine without a
+GPU.  The product never imports this file and has no CPU path; the kernels themselves are checked on the GPU (-m gpu)."""
 
 import torch
 
@@ -63,17 +63,22 @@ def layernorm_fwd(x, gamma, beta, round_out, out_half=False):
     mean = x.mean(-1)
     var = x.var(-1, unbiased=False)
     rstd = (var + 1e-5).rsqrt()
-    return ((x - mean[:, None]) * rstd[:, None]) * gamma + beta, mean, rstd
+    y = ((x - mean[:, None]) * rstd[:, None]) * gamma + beta
+    return (y.half() if out_half else y), mean, rstd
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres, round_out=False, want_colsum=False, half_scale=None, dy_scale=None):
+    dy = dy.float()
+    if dy_scale is not None:                 # the fp16 output of a dgrad GEMM still carries the gradient scale
+        dy = dy * dy_scale
     xh = (x - mean[:, None]) * rstd[:, None]
     g = dy * gamma
     dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
     if dres is not None:
         dx = dx + dres
     out = (dx, (dy * xh).sum(0), dy.sum(0))
-    return out + ((dx.sum(0),) if want_colsum else ())
+    out = out + ((dx.sum(0),) if want_colsum else ())
+    return out + ((to_half(dx, half_scale),) if half_scale is not None else ())
 
 
 def colsum(x):
@@ -102,6 +107,95 @@ def attention_causal_bwd(qkv, out, lse, dout, B, N, heads, dh, scale, cond_len, 
         o, _ = _attn(q, B, N, heads, dh, scale, cond_len)
         o.backward(dout)
     return q.grad
+
+
+def _attn_grad(qkv, dout, B, N, heads, dh, scale, cond):
+    with torch.enable_grad():
+        q = qkv.detach().float().clone().requires_grad_(True)
+        o, _ = _attn(q, B, N, heads, dh, scale, cond)
+        o.backward(dout.float())
+    return q.grad
+
+
+# stage-1 cores: no mask == a fully visible prefix of N tokens
+def attention_fwd(qkv, B, N, heads, dh, scale, round_out, out_half=False):
+    o, lse = _attn(qkv.float(), B, N, heads, dh, scale, N)
+    return (o.half() if out_half else o), lse
+
+
+def attention_bwd(qkv, out, lse, dout, B, N, heads, dh, scale, round_out, half_scale=None):
+    dq = _attn_grad(qkv, dout, B, N, heads, dh, scale, N)
+    return to_half(dq, half_scale) if half_scale is not None else dq
+
+
+def attention_f16_fwd(qkv, B, N, heads, dh, scale):
+    o, lse = _attn(qkv.float(), B, N, heads, dh, scale, N)
+    return o.half(), lse
+
+
+def attention_f16_bwd(qkv, out, lse, dout, B, N, heads, dh, scale):
+    return _attn_grad(qkv, dout, B, N, heads, dh, scale, N).clamp(-65504, 65504).half()     # linear in dout: carries its scale
+
+
+def attention_exact_fwd(qkv, B, N, heads, dh, scale):
+    return _attn(qkv, B, N, heads, dh, scale, N)
+
+
+def attention_exact_bwd(qkv, out, lse, dout, B, N, heads, dh, scale):
+    return _attn_grad(qkv, dout, B, N, heads, dh, scale, N)
+
+
+def _pair(p):
+    return (int(p[0]), int(p[1])) if isinstance(p, (tuple, list)) else (int(p), int(p))
+
+
+def patchify(img, p, round_out):
+    B, C, H, W = img.shape
+    ph, pw = _pair(p)
+    gh, gw = H // ph, W // pw
+    return img.reshape(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * ph * pw).contiguous()
+
+
+def unpatchify(tok, bias, B, C, H, W, p):
+    ph, pw = _pair(p)
+    gh, gw = H // ph, W // pw
+    img = tok.reshape(B, gh, gw, C, ph, pw).permute(0, 3, 1, 4, 2, 5).reshape(B, C, H, W)
+    return (img + bias.view(1, C, 1, 1) if bias is not None else img).contiguous()
+
+
+def add_rows_mod(x, table):
+    D = x.shape[-1]
+    flat = x.reshape(-1, D)
+    t = table.reshape(-1, D)
+    return (flat + t[torch.arange(flat.shape[0]) % t.shape[0]]).view_as(x)
+
+
+def _vq_oracle():
+    from oracle import vitvq_oracle as O
+    return O
+
+
+def vq_fwd(z, E, depth, beta, use_norm=True):
+    assert use_norm
+    out, loss, idx = _vq_oracle().vq_forward(z.detach(), E.detach(), beta, depth > 1, depth)
+    return out, loss, idx.reshape(-1, depth)
+
+
+def vq_bwd(z, E, idx, g_out, g_loss, residual, beta, use_norm=True):
+    depth = idx.shape[-1] if idx.dim() == 2 else 1
+    with torch.enable_grad():
+        z_, E_ = z.detach().clone().requires_grad_(True), E.detach().clone().requires_grad_(True)
+        out, loss, _ = _vq_oracle().vq_forward(z_, E_, beta, bool(residual), depth)
+        total = (out * g_out).sum() if g_out is not None else out.sum() * 0
+        if g_loss is not None:
+            total = total + loss * g_loss
+        total.backward()
+    return z_.grad, (E_.grad if E_.grad is not None else torch.zeros_like(E))
+
+
+def vq_embed(E, codes, depth, use_norm=True):
+    q = torch.nn.functional.normalize(E[codes.reshape(-1, depth)], dim=-1)
+    return q.sum(-2)
 
 
 def time_mix_fwd(x, w, T, round_out=False):
@@ -169,7 +263,9 @@ def launch_count():
     return _COUNT[0]
 
 
-NAMES = ("gemm", "splitk_reduce", "round_tf32", "split_tf32_lo", "to_half", "grad_scale", "layernorm_fwd", "layernorm_bwd", "colsum", "attention_causal_fwd",
+NAMES = ("attention_fwd", "attention_bwd", "attention_f16_fwd", "attention_f16_bwd", "attention_exact_fwd", "attention_exact_bwd",
+         "patchify", "unpatchify", "add_rows_mod", "vq_fwd", "vq_bwd", "vq_embed",
+         "gemm", "splitk_reduce", "round_tf32", "split_tf32_lo", "to_half", "grad_scale", "layernorm_fwd", "layernorm_bwd", "colsum", "attention_causal_fwd",
          "attention_causal_bwd", "time_mix_fwd", "time_mix_bwd", "sqrelu", "token_embed_fwd", "token_embed_bwd", "copy_rows",
          "decode_attention", "launch_count")
 
