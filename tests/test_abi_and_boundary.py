@@ -290,3 +290,30 @@ def test_unchanged_cond_transformer_constructs_with_patch_stage2(monkeypatch):
     assert n_opt == len(list(model.transformer.parameters()))
     decay = {id(p) for p in optimizer.param_groups[0]["params"]}
     assert id(model.transformer.head.weight) in decay and id(model.transformer.blocks[0].attn.time_mix) not in decay
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """error convention of the C ABI (include/b200vq.h): a negative return code and a message from b200vq_last_error();
+    argument validation happens before any CUDA call, so it can be exercised on a machine without a GPU"""
+    lib = etb._lib.lib()
+
+    def err():
+        return lib.b200vq_last_error().decode()
+    # stage-2 attention: head size, prefix length
+    assert lib.b200vq_attention_causal_fwd(None, None, None, 1, 16, 2, 48, 0.1, 1, 1, 0, None) < 0 and "32 or 64" in err()
+    assert lib.b200vq_attention_causal_fwd(None, None, None, 1, 16, 2, 64, 0.1, 17, 1, 0, None) < 0 and "cond_len" in err()
+    assert lib.b200vq_attention_causal_bwd(None, None, None, None, None, None, 0, 16, 2, 64, 0.1, 1, 0, 0, None) < 0 and "empty" in err()
+    # stream kernels of stage 2
+    assert lib.b200vq_time_mix_fwd(None, None, None, 10, 3, 64, 0, None) < 0 and "M % T" in err()
+    assert lib.b200vq_time_mix_fwd(None, None, None, 12, 3, 62, 0, None) < 0
+    assert lib.b200vq_sqrelu(None, None, None, 6, 0, 0, None) < 0
+    assert lib.b200vq_sqrelu(None, None, None, 8, 1, 0, None) < 0 and "gradient" in err()
+    assert lib.b200vq_copy_rows(None, None, 2, 9, 5, 6, 0, 5, 64, None) < 0 and "window" in err()
+    assert lib.b200vq_decode_attention(None, None, None, None, 2, 2, 64, 10, 10, 0.1, None) < 0 and "position" in err()
+    assert lib.b200vq_decode_attention(None, None, None, None, 2, 2, 48, 10, 3, 0.1, None) < 0
+    assert lib.b200vq_token_embed_fwd(None, None, None, None, None, None, None, 2, 0, 0, 64, 5, 5, None) < 0
+    # stage 1: quantiser width, LayerNorm row length, attention head size
+    assert lib.b200vq_vq_fwd(None, None, None, None, None, 128, 256, 16, 1, 0.25, 1, None, 0, None) < 0
+    assert lib.b200vq_layernorm_fwd(None, None, None, None, None, None, None, 8, 4096, 0, None) < 0 and "2048" in err()
+    assert lib.b200vq_attention_f16_fwd(None, None, None, 1, 16, 2, 32, 0.1, None) < 0 and "64" in err()
+    assert lib.b200vq_time_mix_bwd_workspace_bytes(130, 64) == 3 * 64 * 4           # ceil(130 / 64) partial rows
