@@ -13,7 +13,8 @@ Precision modes (`set_precision`, env B200VQ_PRECISION):
             Gradient operands are multiplied by a power of two S chosen on the device from the gradient
             entering each transformer stack (`ops.grad_scale`) and every fp32 result is multiplied by 1/S
             in the producing epilogue: exact, and it keeps fp16's exponent range out of the picture.
-            The attention core runs on kind::tf32 from the fp32 qkv matrix.
+            The attention core runs on kind::f16 as well (dim_head 64: attention_f16.cu; other head sizes on the kind::tf32
+            kernels from a tf32-rounded fp32 qkv matrix).
   "tf32"    every GEMM on kind::tf32 with operands rounded to nearest where they are produced
             (round 1's data path).
   "parity"  error-compensated 3xTF32 GEMMs and attention (fp32-grade, ~3-6x slower): the mode the
