@@ -169,6 +169,41 @@ def test_gpt_host_logic_with_emulated_kernels(golden_dir, monkeypatch, mode):
         etb.set_precision(prev)
 
 
+def test_gpt_sampler_filters_match_the_vendored_reference(monkeypatch):
+    """top-k / nucleus filtering and the multinomial draw of GPT.sample (reference stage2/layers.py:228-254): with the kernels
+    emulated and the same torch RNG stream, the replacement draws the codes the live reference class draws"""
+    import enhancing_transformers_b200 as etb
+    S = _vendored_stage2()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emulated_ops
+    emulated_ops.install(monkeypatch)
+    cfg = dict(vocab_cond_size=6, vocab_img_size=64, embed_dim=64, cond_num_tokens=2, img_num_tokens=9, n_heads=2, n_layers=1)
+    torch.manual_seed(7)
+    ref = S.GPT(**cfg).eval()
+    with torch.no_grad():
+        ref.pos_emb_code.normal_(0, 0.3)
+        for p in ref.parameters():
+            if p.dim() == 2:
+                p.mul_(10.0)
+    prev = etb.set_precision("parity")
+    try:
+        mine = etb.GPT(**cfg).eval()
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        conds = torch.randint(0, 6, (3, 2))
+        for kw in (dict(top_k=7), dict(top_p=0.8), dict(top_k=12, top_p=0.6, softmax_temperature=0.7)):
+            torch.manual_seed(123)
+            with torch.no_grad():
+                l_ref, c_ref = ref.sample(conds, use_fp16=False, **kw)
+            torch.manual_seed(123)
+            l_mine, c_mine = mine.sample(conds, use_fp16=False, **kw)
+            assert torch.equal(c_mine, c_ref), kw
+            finite = torch.isfinite(l_ref)
+            assert torch.equal(finite, torch.isfinite(l_mine))
+            torch.testing.assert_close(l_mine[finite], l_ref[finite], rtol=1e-4, atol=1e-5)
+    finally:
+        etb.set_precision(prev)
+
+
 # ------------------------------------------------------------------------------------------- GPU kernels
 def _mask(T, cond, device):
     m = torch.tril(torch.ones(T, T, device=device, dtype=torch.bool))
