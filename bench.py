@@ -141,6 +141,17 @@ def cpu_threads():
     return min(32, os.cpu_count() or 1)
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_run(cfg_name, batch, warmup, steps):
     import torch
     threads = cpu_threads()
@@ -155,7 +166,7 @@ def cpu_reference_run(cfg_name, batch, warmup, steps):
         hp.step(img)
         times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return dict(value=batch / sec, unit=UNIT, cores=threads, kind=hp.kind, host_cpus=os.cpu_count(), ms_per_step=sec * 1e3,
+    return dict(value=batch / sec, unit=UNIT, cores=threads, kind=hp.kind, host_cpus=os.cpu_count(), cpu_model=cpu_model(), ms_per_step=sec * 1e3,
                 sample=f"{warmup} warm-up + {steps} timed fwd+bwd steps of {batch} images, {cfg_name} config, "
                        f"{'reference nn.Modules (oracle/_ref)' if hp.kind == 'reference' else 'oracle port'} on torch CPU fp32, "
                        f"{threads} threads")
@@ -577,6 +588,8 @@ def main():
         guarded("gpu_eager_baseline", lambda: gpu_eager_baseline(args.config, dev))
     if "cpu" in extras:
         guarded("cpu_baseline", lambda: cpu_reference_run(args.config, args.ref_batch, 1, 3))
+        if args.config == "base":      # BASELINE config 1 (imagenet_vitvq_small.yaml, batch 4: the reference's CPU-runnable case)
+            guarded("cpu_baseline_config1", lambda: cpu_reference_run("small", 4, 1, 3))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
